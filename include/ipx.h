@@ -1,0 +1,202 @@
+/* ipx.h -- C ABI of libipx.so, the B200 (sm_100a) query-evaluation path for interpax.
+ *
+ * This is the drop-in boundary.  The reference (f0uriest/interpax) has no FFI seam of
+ * its own -- the path is inline jax.numpy under jax.jit -- so each entry point below
+ * names the reference code whose *body* it replaces (paths relative to the reference
+ * repo).  A binding (jax.ffi custom call, ctypes, ...) marshals arrays into these
+ * calls; see INTEGRATION.md.
+ *
+ * Conventions (all entry points):
+ *   - every data pointer is a DEVICE pointer owned by the caller; outputs are
+ *     pre-allocated by the caller; nothing is allocated, freed or synchronised here;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*) and nowhere else,
+ *     so every call can be captured into a CUDA graph;
+ *   - operands that are *traced* values in the reference (derivative orders, extrap
+ *     flags and fill values, period values: only `method` is static under jit,
+ *     interpax/_spline.py:444,595,808) travel in `ipx_params`, which may live on the
+ *     host (copied into the launch) or on the device (read by the kernel);
+ *   - the return value is IPX_OK or a negative IPX_E* code; nothing aborts or throws;
+ *   - re-entrant and thread-safe: no mutable global state.
+ */
+#ifndef IPX_H_
+#define IPX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IPX_VERSION 100 /* 0.1.0 */
+
+#define IPX_OK 0
+#define IPX_EINVAL (-1)       /* bad argument (null pointer, negative size, bad enum) */
+#define IPX_EUNSUPPORTED (-2) /* valid request this build does not implement */
+#define IPX_ELAUNCH (-3)      /* cudaPeekAtLastError() reported a launch failure */
+
+/* method class: which branch of interp1d/2d/3d runs (interpax/_spline.py:529,540,569).
+ * All of cubic/cubic2/cardinal/catmull-rom/akima/monotonic/monotonic-0 are IPX_CUBIC:
+ * they differ only in how the slope tables were produced (ipx_slopes_*). */
+#define IPX_NEAREST 0
+#define IPX_LINEAR 1
+#define IPX_CUBIC 2
+
+/* periodic_mask helpers */
+#define IPX_PERIODIC(axis) (1 << (axis))
+#define IPX_WRAP_ONLY(axis) (1 << (4 + (axis)))
+
+/* table layouts accepted by the evaluation kernels */
+#define IPX_SOA 0 /* the reference's layout: 2^d separate C-order arrays (f, fx, ...)  */
+#define IPX_AOS 1 /* one record per node written by ipx_pack*: see DESIGN.md "Data layout" */
+
+/* slope stencils of approx_df (interpax/_fd_derivs.py:44-75) */
+#define IPX_SLOPE_CUBIC 0       /* _cubic1      _fd_derivs.py:79-101  */
+#define IPX_SLOPE_CUBIC2 1      /* _cubic2      _fd_derivs.py:160-300 */
+#define IPX_SLOPE_CARDINAL 2    /* _cardinal    _fd_derivs.py:303-324 (catmull-rom: c = 0) */
+#define IPX_SLOPE_MONOTONIC 3   /* _monotonic   _fd_derivs.py:327-387 */
+#define IPX_SLOPE_MONOTONIC0 4  /* _monotonic, zero end slopes */
+#define IPX_SLOPE_AKIMA 5       /* _akima       _fd_derivs.py:390-424 */
+#define IPX_SLOPE_ZERO 6        /* nearest / linear -> zeros, _fd_derivs.py:72-73 */
+
+/* cubic2 boundary conditions (_fd_derivs.py:104-157) */
+#define IPX_BC_NOT_A_KNOT 0
+#define IPX_BC_FIRST 1  /* (1, value); "clamped" = value NULL (zeros) */
+#define IPX_BC_SECOND 2 /* (2, value); "natural" = value NULL (zeros) */
+
+/* Per-axis run-time operands (traced in the reference). */
+typedef struct ipx_axis_params {
+  int32_t derivative;  /* order along this axis; >= 4 gives zeros, < 0 acts as 0
+                          (lax.switch clamps, _spline.py:1151)                         */
+  int32_t keep_lo;     /* 1: extrap=True below x[0] (polynomial continues); 0: fill    */
+  int32_t keep_hi;     /* same above x[-1]                                             */
+  int32_t reserved;
+  double fill_lo;      /* value written where q < x[0] when keep_lo == 0 (NaN for
+                          extrap=False, the number for a numeric extrap)  _spline.py:1190-1220 */
+  double fill_hi;
+  double period;       /* |period| is used, and only on axes named in periodic_mask    */
+} ipx_axis_params;
+
+typedef struct ipx_params {
+  ipx_axis_params axis[3];
+} ipx_params;
+
+typedef struct ipx_slope_opts {
+  double c;                  /* cardinal tension, kwarg `c` (_fd_derivs.py:51)          */
+  int32_t bc_start, bc_end;  /* IPX_BC_* for cubic2, kwarg `bc_type` (_fd_derivs.py:47) */
+  const void* bc_start_value; /* device, outer*inner values of T, or NULL for zeros     */
+  const void* bc_end_value;
+} ipx_slope_opts;
+
+int ipx_version(void);
+/* Static description of the build: "sm_100a" etc.  Never NULL. */
+const char* ipx_build_info(void);
+
+/* ---------------------------------------------------------------------------------
+ * Query evaluation.  Replaces the bodies of
+ *   interp1d  interpax/_spline.py:529-592   (search, gather, A_CUBIC contraction, extrap)
+ *   interp2d  interpax/_spline.py:702-805
+ *   interp3d  interpax/_spline.py:940-1105
+ * including _get_t_der (:1138-1151), _extrap (:1180-1222) and, through the knot/perm
+ * arguments, the table side of _make_periodic (:1108-1135) without copying any table.
+ *
+ *   q*          nq query coordinates per axis (already broadcast to a common length)
+ *   knots*      n knots of that axis; on an axis named in periodic_mask, the n+2 padded,
+ *               sorted knots written by ipx_periodic_knots_*
+ *   perm*       NULL, or (periodic axes) n int32: sorted position -> table index
+ *   n*          extent of the tables along the axis (un-padded)
+ *   tables      HOST array of device pointers.  IPX_SOA: 2^d tables in the reference's
+ *               stacking order (1-D: f, fx; 2-D: f, fx, fy, fxy; 3-D: f, fx, fy, fz, fxy,
+ *               fxz, fyz, fxyz -- _spline.py:581-584, 779-783, 1070-1078), each of shape
+ *               (nx[,ny[,nz]], batch) C-order; for IPX_NEAREST / IPX_LINEAR only
+ *               tables[0] is read.  IPX_AOS: tables[0] is the packed array.
+ *   batch       product of f's trailing dimensions (>= 1); out is (nq, batch)
+ *   periodic_mask  bit a set: axis a is periodic (queries are wrapped with the Python
+ *               remainder in the kernel; extrapolation flags of that axis are ignored,
+ *               _spline.py:527).  Bit 4+a set instead (IPX_WRAP_ONLY): the caller has
+ *               already materialised the padded knots AND padded tables of that axis
+ *               (ipx_pad_periodic_*), n is the padded extent, and the kernel only wraps
+ *               the query.
+ *   params      see ipx_params; params_on_device != 0 means a device pointer
+ *   out         (nq, batch) results
+ *   idx_out     NULL or (d, nq) int32: the interval index i = clip(searchsorted(knots, q,
+ *               side="right"), 1, len-1) per axis, in padded coordinates on periodic
+ *               axes (_spline.py:571, 767-768, 1051-1053) -- for bit-exact index parity
+ * --------------------------------------------------------------------------------- */
+#define IPX_DECL_EVAL(SUF, T)                                                                   \
+  int ipx_eval1d_##SUF(const T* xq, int64_t nq, const T* x, const int32_t* permx, int32_t nx,   \
+                       const T* const* tables, int32_t layout, int64_t batch,                   \
+                       int32_t method_class, int32_t periodic_mask, const ipx_params* params,   \
+                       int32_t params_on_device, T* out, int32_t* idx_out, void* stream);       \
+  int ipx_eval2d_##SUF(const T* xq, const T* yq, int64_t nq, const T* x, const T* y,            \
+                       const int32_t* permx, const int32_t* permy, int32_t nx, int32_t ny,      \
+                       const T* const* tables, int32_t layout, int64_t batch,                   \
+                       int32_t method_class, int32_t periodic_mask, const ipx_params* params,   \
+                       int32_t params_on_device, T* out, int32_t* idx_out, void* stream);       \
+  int ipx_eval3d_##SUF(const T* xq, const T* yq, const T* zq, int64_t nq, const T* x,           \
+                       const T* y, const T* z, const int32_t* permx, const int32_t* permy,      \
+                       const int32_t* permz, int32_t nx, int32_t ny, int32_t nz,                \
+                       const T* const* tables, int32_t layout, int64_t batch,                   \
+                       int32_t method_class, int32_t periodic_mask, const ipx_params* params,   \
+                       int32_t params_on_device, T* out, int32_t* idx_out, void* stream);
+
+IPX_DECL_EVAL(f32, float)
+IPX_DECL_EVAL(f64, double)
+
+/* ---------------------------------------------------------------------------------
+ * Interval lookup alone: idx[k] = clip(searchsorted(knots, q[k], side="right"), 1, n-1).
+ * Replaces the jnp.searchsorted + jnp.clip pair at interpax/_spline.py:543,556,571,
+ * 708-709,729-730,767-768,946-948,983-985,1051-1053.
+ * --------------------------------------------------------------------------------- */
+int ipx_bin_index_f32(const float* knots, int32_t n, const float* q, int64_t nq, int32_t* idx,
+                      void* stream);
+int ipx_bin_index_f64(const double* knots, int32_t n, const double* q, int64_t nq, int32_t* idx,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Slope precompute: out = approx_df(x, f, method, axis) for a C-contiguous table viewed
+ * as (outer, n, inner) with the differentiated axis in the middle.
+ * Replaces interpax/_fd_derivs.py:9-443 (one call per link of the chains at
+ * _spline.py:119-122, 237-244, 380-393, 572-573, 759-764, 1027-1040).
+ * `workspace` must hold ipx_slopes_workspace_bytes(...) bytes (device memory).
+ * --------------------------------------------------------------------------------- */
+size_t ipx_slopes_workspace_bytes(int32_t method, int32_t n, int32_t elem_size);
+int ipx_slopes_f32(const float* x, int32_t n, const float* f, int64_t outer, int64_t inner,
+                   int32_t method, const ipx_slope_opts* opts, float* out, void* workspace,
+                   void* stream);
+int ipx_slopes_f64(const double* x, int32_t n, const double* f, int64_t outer, int64_t inner,
+                   int32_t method, const ipx_slope_opts* opts, double* out, void* workspace,
+                   void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Periodic axis preparation -- the knot side of _make_periodic, interpax/_spline.py:
+ * 1117-1122: xm = x % |period|; perm = stable argsort(xm); xpad = [xs[-1]-P, xs..., xs[0]+P].
+ * xpad has n+2 entries, perm n.  `workspace` holds (n + 4) * elem_size bytes.
+ * --------------------------------------------------------------------------------- */
+int ipx_periodic_knots_f32(const float* x, int32_t n, double period, float* xpad, int32_t* perm,
+                           void* workspace, void* stream);
+int ipx_periodic_knots_f64(const double* x, int32_t n, double period, double* xpad,
+                           int32_t* perm, void* workspace, void* stream);
+
+/* Materialised wrap-pad of one table along one axis, for the functional form that
+ * differentiates *after* padding (interpax/_spline.py:1123-1135 followed by :1027-1040):
+ * out[o, p, i] = in[o, perm[(p-1) mod n], i], p in [0, n+2). */
+int ipx_pad_periodic_f32(const float* in, int64_t outer, int32_t n, int64_t inner,
+                         const int32_t* perm, float* out, void* stream);
+int ipx_pad_periodic_f64(const double* in, int64_t outer, int32_t n, int64_t inner,
+                         const int32_t* perm, double* out, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Interleave the 2^d SoA tables into the IPX_AOS layout (one record of 2^d values per
+ * (node, batch element)); record order in DESIGN.md.  `tables` is a HOST array of 2^d
+ * device pointers in the reference's stacking order; nodes = nx*ny*nz.
+ * --------------------------------------------------------------------------------- */
+int ipx_pack_f32(int32_t ndim, const float* const* tables, int64_t nodes_times_batch, float* out,
+                 void* stream);
+int ipx_pack_f64(int32_t ndim, const double* const* tables, int64_t nodes_times_batch,
+                 double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPX_H_ */

@@ -1,0 +1,63 @@
+"""In-tree build of libipx.so (hand-written CUDA for sm_100a behind the C ABI of include/ipx.h).
+
+``python -m interpax_b200._build`` or ``build()`` compiles ``csrc/*.cu`` with nvcc into
+``interpax_b200/libipx.so``.  The .so is git-ignored but travels with the tree to the GPU
+box; nothing is JIT-compiled into a user cache.
+"""
+
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libipx.so")
+SOURCES = ["ipx_eval.cu", "ipx_slopes.cu", "ipx_prep.cu"]
+HEADERS = [os.path.join(CSRC, "ipx_device.cuh"), os.path.join(HERE, "..", "include", "ipx.h")]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def find_nvcc() -> str | None:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    return None
+
+
+def is_stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile libipx.so if it is missing or older than its sources. Returns its path."""
+    if not force and not is_stale():
+        return LIB
+    nvcc = find_nvcc()
+    if nvcc is None:
+        raise RuntimeError("nvcc not found: cannot build interpax_b200/libipx.so")
+    cmd = [nvcc, *NVCC_FLAGS]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += ["-o", LIB + ".tmp"] + [os.path.join(CSRC, s) for s in SOURCES]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
+    os.replace(LIB + ".tmp", LIB)
+    if verbose:
+        sys.stderr.write(proc.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

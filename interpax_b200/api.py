@@ -1,0 +1,701 @@
+"""Host side of the interpax query path on B200: the reference's call signatures on top of
+the C ABI (include/ipx.h, libipx.so).
+
+Mirrors (reference repo paths):
+  interp1d / interp2d / interp3d            interpax/_spline.py:444-1105
+  Interpolator1D / 2D / 3D                  interpax/_spline.py:48-441
+  approx_df                                 interpax/_fd_derivs.py:9-76
+with the same argument meaning, dtype promotion (utils.py:42-50, _spline.py:503-506),
+output shapes and ValueError texts.  All arithmetic happens in the CUDA kernels; this
+file only parses arguments and moves arrays.  PyTorch is used for device memory and
+streams, nothing else.  Inputs may be NumPy arrays / Python scalars (results come back
+as NumPy arrays: host -> device -> host) or torch tensors (results stay on the device).
+
+There is no CPU fallback: without a CUDA device or without libipx.so every call raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Any
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+CUBIC_METHODS = ("cubic", "cubic2", "cardinal", "catmull-rom", "akima", "monotonic", "monotonic-0")
+OTHER_METHODS = ("nearest", "linear")
+METHODS_1D = METHODS_2D = METHODS_3D = CUBIC_METHODS + OTHER_METHODS
+
+# the reference's stacking order of the slope tables (_spline.py:581-584, 779-783, 1070-1078)
+TABLES = {
+    1: ("f", "fx"),
+    2: ("f", "fx", "fy", "fxy"),
+    3: ("f", "fx", "fy", "fz", "fxy", "fxz", "fyz", "fxyz"),
+}
+# chain used to fill in missing tables: name -> (source table, axis)
+# (_spline.py:119-122, 237-244, 380-393, 572-573, 759-764, 1027-1040)
+CHAIN = {
+    1: (("fx", "f", 0),),
+    2: (("fx", "f", 0), ("fy", "f", 1), ("fxy", "fx", 1)),
+    3: (
+        ("fx", "f", 0), ("fy", "f", 1), ("fz", "f", 2), ("fxy", "fx", 1),
+        ("fxz", "fx", 2), ("fyz", "fy", 2), ("fxyz", "fxy", 2),
+    ),
+}
+_SLOPE_CODE = {
+    "cubic": L.IPX_SLOPE_CUBIC, "cubic2": L.IPX_SLOPE_CUBIC2, "cardinal": L.IPX_SLOPE_CARDINAL,
+    "catmull-rom": L.IPX_SLOPE_CARDINAL, "monotonic": L.IPX_SLOPE_MONOTONIC,
+    "monotonic-0": L.IPX_SLOPE_MONOTONIC0, "akima": L.IPX_SLOPE_AKIMA,
+    "nearest": L.IPX_SLOPE_ZERO, "linear": L.IPX_SLOPE_ZERO,
+}
+_NP2T = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
+         np.dtype(np.complex64): torch.complex64, np.dtype(np.complex128): torch.complex128}
+_T2NP = {
+    torch.float16: np.dtype(np.float16), torch.bfloat16: np.dtype(np.float32),
+    torch.float32: np.dtype(np.float32), torch.float64: np.dtype(np.float64),
+    torch.complex64: np.dtype(np.complex64), torch.complex128: np.dtype(np.complex128),
+    torch.int8: np.dtype(np.int8), torch.int16: np.dtype(np.int16), torch.int32: np.dtype(np.int32),
+    torch.int64: np.dtype(np.int64), torch.uint8: np.dtype(np.uint8), torch.bool: np.dtype(np.bool_),
+}
+
+
+# --------------------------------------------------------------------------- small helpers
+def isbool(x: Any) -> bool:
+    """utils.py:17-19."""
+    return isinstance(x, bool) or (hasattr(x, "dtype") and (x.dtype == bool or x.dtype == torch.bool))
+
+
+def errorif(cond, err=ValueError, msg=""):
+    """utils.py:22-31."""
+    if cond:
+        raise err(msg)
+
+
+def _device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "interpax_b200 needs a CUDA device: the query path is hand-written CUDA behind "
+            "libipx.so and has no CPU fallback"
+        )
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _is_pyscalar(a) -> bool:
+    return isinstance(a, (bool, int, float, complex))
+
+
+def _np_dtype_of(a) -> np.dtype:
+    if isinstance(a, torch.Tensor):
+        return _T2NP[a.dtype]
+    return np.asarray(a).dtype
+
+
+def _inexact(dt: np.dtype) -> np.dtype:
+    """asarray_inexact (utils.py:42-50): integer / bool inputs become the default float."""
+    if not np.issubdtype(dt, np.inexact):
+        return np.dtype(np.float64)
+    if dt == np.float16:
+        return np.dtype(np.float32)
+    return dt
+
+
+def _promote(items) -> np.dtype:
+    """result_type with Python scalars weakly typed, as in JAX (utils.py:45-46)."""
+    parts = [a if _is_pyscalar(a) else _inexact(_np_dtype_of(a)) for a in items]
+    dt = np.result_type(*parts)
+    return _inexact(np.dtype(dt))
+
+
+def _to_dev(a, np_dt: np.dtype, dev: torch.device) -> torch.Tensor:
+    tdt = _NP2T[np.dtype(np_dt)]
+    if isinstance(a, torch.Tensor):
+        return a.to(device=dev, dtype=tdt).contiguous()
+    arr = np.ascontiguousarray(np.asarray(a, dtype=np_dt))
+    return torch.from_numpy(arr).to(dev)
+
+
+def _parse_ndarg(arg, n):
+    """_spline.py:1154-1161."""
+    try:
+        k = len(arg)
+    except TypeError:
+        arg = tuple(arg for _ in range(n))
+        k = n
+    assert k == n, "got too many args"
+    return tuple(arg)
+
+
+def _isscalar(v) -> bool:
+    return np.isscalar(v) or (isinstance(v, (np.ndarray, torch.Tensor)) and v.ndim == 0)
+
+
+def _parse_extrap(extrap, n):
+    """_spline.py:1164-1177."""
+    if isbool(extrap):
+        return tuple(extrap for _ in range(2 * n))
+    elif _isscalar(extrap):
+        return tuple(extrap for _ in range(2 * n))
+    elif len(extrap) == 2 and _isscalar(extrap[0]):
+        return tuple(e for _ in range(n) for e in extrap)
+    elif len(extrap) == n and all(len(extrap[i]) == 2 for i in range(n)):
+        return tuple(eij for ei in extrap for eij in ei)
+    raise ValueError(
+        "extrap should either be a scalar, 2 element sequence (lo, hi), "
+        + "or a sequence with 2 elements for each dimension"
+    )
+
+
+def _keep_fill(e):
+    """One side of `extrap` -> (keep flag, fill value) of ipx_axis_params (_spline.py:1190-1220)."""
+    if isbool(e):
+        return (1, 0.0) if bool(e) else (0, math.nan)
+    return 0, float(e)
+
+
+def _ptr(t: torch.Tensor | None):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _ptr_array(ts):
+    arr = (C.c_void_p * len(ts))()
+    for k, t in enumerate(ts):
+        arr[k] = None if t is None else t.data_ptr()
+    return arr
+
+
+def _suffix(t: torch.Tensor) -> str:
+    return "f32" if t.dtype == torch.float32 else "f64"
+
+
+# --------------------------------------------------------------------------- device-side ops
+def _slopes_dev(x: torch.Tensor, f: torch.Tensor, method: str, axis: int, kwargs: dict) -> torch.Tensor:
+    """approx_df on device tensors (real dtype, C-contiguous)."""
+    errorif(method not in _SLOPE_CODE, ValueError, f"got unknown method {method}")
+    lib = L.load()
+    axis = axis % f.ndim
+    n = f.shape[axis]
+    errorif(x.ndim != 1 or x.shape[0] != n, ValueError, "x and f must be arrays of equal length")
+    outer = int(np.prod(f.shape[:axis], dtype=np.int64))
+    inner = int(np.prod(f.shape[axis + 1:], dtype=np.int64))
+    code = _SLOPE_CODE[method]
+    opts = L.SlopeOpts()
+    opts.c = float(kwargs.get("c", 0)) if method == "cardinal" else 0.0
+    keep = []
+    if method == "cubic2":
+        bcs = _validate_bc(kwargs.get("bc_type", "not-a-knot"), f.shape[:axis] + f.shape[axis + 1:])
+        kinds, vals = [], []
+        for kind, val in bcs:
+            kinds.append(kind)
+            if val is None:
+                vals.append(None)
+            else:
+                v = _to_dev(val, _T2NP[f.dtype], f.device).reshape(-1)
+                keep.append(v)
+                vals.append(v.data_ptr())
+        opts.bc_start, opts.bc_end = kinds
+        opts.bc_start_value, opts.bc_end_value = vals
+    out = torch.empty_like(f)
+    elem = f.element_size()
+    wbytes = lib.ipx_slopes_workspace_bytes(code, n, elem)
+    ws = torch.empty(max(int(wbytes), 16), dtype=torch.uint8, device=f.device)
+    fn = getattr(lib, f"ipx_slopes_{_suffix(f)}")
+    L.check(
+        fn(_ptr(x), n, _ptr(f), outer, inner, code, C.byref(opts), _ptr(out), _ptr(ws), _stream()),
+        "ipx_slopes",
+    )
+    return out
+
+
+def _validate_bc(bc_type, expected_shape):
+    """_fd_derivs.py:104-157 -> [(IPX_BC_*, value-or-None)] * 2."""
+    if isinstance(bc_type, str):
+        errorif(bc_type == "periodic", NotImplementedError)
+        bc_type = (bc_type, bc_type)
+    else:
+        errorif(
+            len(bc_type) != 2, ValueError,
+            "`bc_type` must contain 2 elements to specify start and end conditions.",
+        )
+        errorif(
+            any(isinstance(b, str) and b == "periodic" for b in bc_type), ValueError,
+            "'periodic' `bc_type` is defined for both curve ends and cannot be used with other "
+            "boundary conditions.",
+        )
+    out = []
+    for bc in bc_type:
+        if isinstance(bc, str):
+            if bc == "clamped":
+                out.append((L.IPX_BC_FIRST, None))
+            elif bc == "natural":
+                out.append((L.IPX_BC_SECOND, None))
+            elif bc == "not-a-knot":
+                out.append((L.IPX_BC_NOT_A_KNOT, None))
+            else:
+                raise ValueError(f"bc_type={bc} is not allowed.")
+        else:
+            try:
+                order, value = bc
+            except Exception as e:
+                raise ValueError(
+                    "A specified derivative value must be given in the form (order, value)."
+                ) from e
+            if order not in [1, 2]:
+                raise ValueError("The specified derivative order must be 1 or 2.")
+            shape = tuple(value.shape) if hasattr(value, "shape") else np.shape(value)
+            if tuple(shape) != tuple(expected_shape):
+                raise ValueError(
+                    "`deriv_value` shape {} is not the expected one {}.".format(
+                        tuple(shape), tuple(expected_shape)
+                    )
+                )
+            out.append((L.IPX_BC_FIRST if order == 1 else L.IPX_BC_SECOND, value))
+    return out
+
+
+def _periodic_knots_dev(x: torch.Tensor, period: float):
+    """Knot side of _make_periodic (_spline.py:1117-1122) -> (xpad[n+2], perm[n])."""
+    lib = L.load()
+    n = x.shape[0]
+    xpad = torch.empty(n + 2, dtype=x.dtype, device=x.device)
+    perm = torch.empty(n, dtype=torch.int32, device=x.device)
+    ws = torch.empty((n + 4) * x.element_size(), dtype=torch.uint8, device=x.device)
+    fn = getattr(lib, f"ipx_periodic_knots_{_suffix(x)}")
+    L.check(fn(_ptr(x), n, abs(float(period)), _ptr(xpad), _ptr(perm), _ptr(ws), _stream()),
+            "ipx_periodic_knots")
+    return xpad, perm
+
+
+def _pad_periodic_dev(t: torch.Tensor, axis: int, perm: torch.Tensor) -> torch.Tensor:
+    """Materialised table side of _make_periodic (_spline.py:1123-1135)."""
+    lib = L.load()
+    n = t.shape[axis]
+    outer = int(np.prod(t.shape[:axis], dtype=np.int64))
+    inner = int(np.prod(t.shape[axis + 1:], dtype=np.int64))
+    shape = list(t.shape)
+    shape[axis] = n + 2
+    out = torch.empty(shape, dtype=t.dtype, device=t.device)
+    fn = getattr(lib, f"ipx_pad_periodic_{_suffix(t)}")
+    L.check(fn(_ptr(t), outer, n, inner, _ptr(perm), _ptr(out), _stream()), "ipx_pad_periodic")
+    return out
+
+
+def _pack_dev(ndim: int, tabs: list[torch.Tensor]) -> torch.Tensor:
+    """SoA -> AoS interleave; record layout in DESIGN.md."""
+    lib = L.load()
+    f = tabs[0]
+    total = f.numel()
+    out = torch.empty(tuple(f.shape) + (1 << ndim,), dtype=f.dtype, device=f.device)
+    fn = getattr(lib, f"ipx_pack_{_suffix(f)}")
+    L.check(fn(ndim, _ptr_array(tabs), total, _ptr(out), _stream()), "ipx_pack")
+    return out
+
+
+def _make_params(ndim, derivative, extrap6, periods) -> L.Params:
+    p = L.Params()
+    for ax in range(ndim):
+        a = p.axis[ax]
+        a.derivative = int(derivative[ax])
+        a.keep_lo, a.fill_lo = _keep_fill(extrap6[2 * ax])
+        a.keep_hi, a.fill_hi = _keep_fill(extrap6[2 * ax + 1])
+        a.period = abs(float(periods[ax])) if periods[ax] is not None else 0.0
+    return p
+
+
+def _eval_dev(ndim, qs, knots, perms, ns, tables, layout, batch, method_class, periodic_mask,
+              params, return_index=False):
+    """One call into ipx_eval{1,2,3}d_*; everything is a device tensor already."""
+    lib = L.load()
+    nq = qs[0].numel()
+    dt = qs[0].dtype
+    out = torch.empty((nq, batch), dtype=dt, device=qs[0].device)
+    idx = torch.empty((ndim, nq), dtype=torch.int32, device=qs[0].device) if return_index else None
+    fn = getattr(lib, f"ipx_eval{ndim}d_{_suffix(qs[0])}")
+    args = [_ptr(q) for q in qs] + [nq] + [_ptr(k) for k in knots] + [_ptr(p) for p in perms]
+    args += [int(n) for n in ns]
+    args += [_ptr_array(tables), layout, batch, method_class, periodic_mask, C.byref(params), 0,
+             _ptr(out), _ptr(idx), _stream()]
+    L.check(fn(*args), f"ipx_eval{ndim}d")
+    return out, idx
+
+
+# --------------------------------------------------------------------------- front end
+class _Inputs:
+    """dtype / shape front matter shared by the functional and class forms
+    (_spline.py:503-521, 663-689, 882-910)."""
+
+    def __init__(self, ndim, qs, knots, f, extra_tables=()):
+        self.want_torch = any(isinstance(a, torch.Tensor) for a in (*qs, *knots, f))
+        self.dev = _device()
+        self.xdt = _promote([*knots, *qs])
+        errorif(np.issubdtype(self.xdt, np.complexfloating), TypeError, "knots and queries must be real")
+        self.fdt = np.dtype(np.result_type(_promote([f]), self.xdt))
+        self.complex = bool(np.issubdtype(self.fdt, np.complexfloating))
+        # the kernels compute in one real type T = the real part of result_type(f, x)
+        self.rdt = np.dtype(np.float64) if self.fdt in (np.float64, np.complex128) else np.dtype(np.float32)
+
+    def coords(self, a):
+        t = _to_dev(a, self.xdt, self.dev)
+        return t if self.rdt == self.xdt else t.to(_NP2T[self.rdt])
+
+    def table(self, a):
+        t = _to_dev(a, self.fdt, self.dev)
+        if self.complex:
+            t = torch.view_as_real(t).contiguous()
+        return t if t.dtype == _NP2T[self.rdt] else t.to(_NP2T[self.rdt])
+
+    def finish(self, out: torch.Tensor, outshape):
+        if self.complex:
+            out = torch.view_as_complex(out.reshape(tuple(outshape) + (2,)).contiguous())
+        out = out.reshape(tuple(outshape))
+        tdt = _NP2T[self.fdt]
+        if out.dtype != tdt:
+            out = out.to(tdt)
+        return out if self.want_torch else out.cpu().numpy()
+
+
+def _shape(a):
+    return tuple(a.shape) if hasattr(a, "shape") else np.shape(a)
+
+
+def _check_shapes(ndim, knots, fshape):
+    """The reference's argument checks (_spline.py:516-521, 679-689, 887-902); they need no
+    device, so bad calls fail the same way with or without a GPU."""
+    errorif(len(fshape) < ndim, ValueError, "x and f must be arrays of equal length")
+    for ax, name in zip(range(ndim), "xyz"):
+        ks = _shape(knots[ax])
+        errorif(
+            (len(ks) != 1) or (ks[0] != fshape[ax]), ValueError,
+            f"{name} and f must be arrays of equal length",
+        )
+
+
+def _method_class(method):
+    return L.IPX_NEAREST if method == "nearest" else L.IPX_LINEAR if method == "linear" else L.IPX_CUBIC
+
+
+def _interp(ndim, qs, knots, f, method, derivative, extrap, period, kwargs, return_index=False):
+    """Functional form.  Body of interp1d/2d/3d (_spline.py:503-592, 663-805, 882-1105)."""
+    methods = (METHODS_1D, METHODS_2D, METHODS_3D)[ndim - 1]
+    names = TABLES[ndim]
+    kwargs = dict(kwargs)
+    given = {n: kwargs.pop(n, None) for n in names[1:]}
+    if ndim == 1:
+        axis = kwargs.get("axis", 0)
+        errorif(axis != 0, NotImplementedError, "only axis=0 is supported")
+    kwargs.pop("axis", None)
+
+    fshape_user = _shape(f)
+    _check_shapes(ndim, knots, fshape_user)
+    errorif(method not in methods, ValueError, f"unknown method {method}")
+    io = _Inputs(ndim, qs, knots, f, given.values())
+    kn = [io.coords(k) for k in knots]
+    errorif(io.complex and method == "akima" and any(v is None for v in given.values()),
+            NotImplementedError, "akima slopes of complex data are not implemented")
+
+    qd = [io.coords(q) for q in qs]
+    qd = list(torch.broadcast_tensors(*qd)) if ndim > 1 else qd
+    outshape = tuple(qd[0].shape) + tuple(fshape_user[ndim:])
+    qd = [q.contiguous().reshape(-1) for q in qd]
+
+    periods = _parse_ndarg(period, ndim)
+    derivs = _parse_ndarg(derivative, ndim)
+    ex = _parse_extrap(extrap, ndim)
+
+    tabs = {"f": io.table(f)}
+    for n in names[1:]:
+        tabs[n] = None if given[n] is None else io.table(given[n])
+    batch = int(np.prod(tabs["f"].shape[ndim:], dtype=np.int64))
+    mclass = _method_class(method)
+
+    pk = [None] * ndim  # per periodic axis: (xpad, perm)
+    for ax in range(ndim):
+        if periods[ax] is not None:
+            pk[ax] = _periodic_knots_dev(kn[ax], periods[ax])
+
+    mask = 0
+    perms = [None] * ndim
+    kuse = list(kn)
+    if mclass == L.IPX_CUBIC:
+        missing = [n for n in names[1:] if tabs[n] is None]
+        if missing and any(p is not None for p in pk):
+            # the functional form differentiates the PADDED tables (_spline.py:924-938 then
+            # :1027-1040): materialise the pad, then evaluate with wrap-only axes.
+            for ax in range(ndim):
+                if pk[ax] is None:
+                    continue
+                for n in names:
+                    if tabs[n] is not None:
+                        tabs[n] = _pad_periodic_dev(tabs[n], ax, pk[ax][1])
+                kuse[ax] = pk[ax][0]
+                mask |= L.IPX_WRAP_ONLY(ax)
+        else:
+            for ax in range(ndim):
+                if pk[ax] is not None:
+                    kuse[ax], perms[ax] = pk[ax]
+                    mask |= L.IPX_PERIODIC(ax)
+        for name, src, ax in CHAIN[ndim]:
+            if tabs[name] is None:
+                tabs[name] = _slopes_dev(kuse[ax], tabs[src], method, ax, kwargs)
+        for n in names[1:]:
+            errorif(tabs[n].shape != tabs["f"].shape, ValueError,
+                    f"{n} must have the same shape as f")
+        tables = [tabs[n] for n in names]
+    else:
+        for ax in range(ndim):
+            if pk[ax] is not None:
+                kuse[ax], perms[ax] = pk[ax]
+                mask |= L.IPX_PERIODIC(ax)
+        tables = [tabs["f"]]
+
+    ns = [tabs["f"].shape[ax] for ax in range(ndim)]
+    params = _make_params(ndim, derivs, ex, periods)
+    out, idx = _eval_dev(ndim, qd, kuse, perms, ns, tables, L.IPX_SOA, batch, mclass, mask, params,
+                         return_index)
+    res = io.finish(out, outshape)
+    if return_index:
+        return res, (idx if io.want_torch else idx.cpu().numpy())
+    return res
+
+
+def interp1d(xq, x, f, method="cubic", derivative=0, extrap=False, period=None, **kwargs):
+    """Interpolate a 1d function.  Same contract as interpax.interp1d (_spline.py:445-592):
+    ``xq`` (Nq,), ``x`` (Nx,), ``f`` (Nx, ...), ``method`` one of nearest / linear / cubic /
+    cubic2 / catmull-rom / cardinal / monotonic / monotonic-0 / akima, ``derivative`` >= 0,
+    ``extrap`` bool | float | (lo, hi), ``period`` None | float, kwargs ``fx``, ``c``,
+    ``bc_type``.  Returns (Nq, ...)."""
+    return _interp(1, (xq,), (x,), f, method, derivative, extrap, period, kwargs)
+
+
+def interp2d(xq, yq, x, y, f, method="cubic", derivative=0, extrap=False, period=None, **kwargs):
+    """Interpolate a 2d function.  Same contract as interpax.interp2d (_spline.py:596-805);
+    kwargs ``fx``, ``fy``, ``fxy``, ``c``, ``bc_type``."""
+    return _interp(2, (xq, yq), (x, y), f, method, derivative, extrap, period, kwargs)
+
+
+def interp3d(xq, yq, zq, x, y, z, f, method="cubic", derivative=0, extrap=False, period=None,
+             **kwargs):
+    """Interpolate a 3d function.  Same contract as interpax.interp3d (_spline.py:809-1105);
+    kwargs ``fx`` ... ``fxyz``, ``c``, ``bc_type``."""
+    return _interp(3, (xq, yq, zq), (x, y, z), f, method, derivative, extrap, period, kwargs)
+
+
+def approx_df(x, f, method="cubic", axis=-1, **kwargs):
+    """First derivatives at the knots.  Same contract as interpax.approx_df
+    (_fd_derivs.py:9-76)."""
+    want_torch = isinstance(x, torch.Tensor) or isinstance(f, torch.Tensor)
+    dev = _device()
+    fdt = _promote([f])
+    xdt = _promote([x])
+    cplx = bool(np.issubdtype(fdt, np.complexfloating))
+    errorif(cplx and method == "akima", NotImplementedError,
+            "akima slopes of complex data are not implemented")
+    rdt = np.dtype(np.float64) if fdt in (np.float64, np.complex128) else np.dtype(np.float32)
+    ft = _to_dev(f, fdt, dev)
+    nd = ft.ndim
+    axis = axis % nd
+    if cplx:
+        ft = torch.view_as_real(ft).contiguous()
+    xt = _to_dev(x, xdt, dev).to(_NP2T[rdt])
+    out = _slopes_dev(xt, ft, method, axis, kwargs)
+    if cplx:
+        out = torch.view_as_complex(out)
+    return out if want_torch else out.cpu().numpy()
+
+
+def bin_index(x, q):
+    """``clip(searchsorted(x, q, side="right"), 1, len(x)-1)`` on the device -- the interval
+    lookup of _spline.py:571 on its own (int32)."""
+    want_torch = isinstance(x, torch.Tensor) or isinstance(q, torch.Tensor)
+    dev = _device()
+    dt = _promote([x, q])
+    xt, qt = _to_dev(x, dt, dev), _to_dev(q, dt, dev)
+    shape = qt.shape
+    qt = qt.reshape(-1)
+    idx = torch.empty(qt.numel(), dtype=torch.int32, device=dev)
+    lib = L.load()
+    fn = getattr(lib, f"ipx_bin_index_{_suffix(xt)}")
+    L.check(fn(_ptr(xt), xt.shape[0], _ptr(qt), qt.numel(), _ptr(idx), _stream()), "ipx_bin_index")
+    idx = idx.reshape(shape)
+    return idx if want_torch else idx.cpu().numpy()
+
+
+# --------------------------------------------------------------------------- containers
+class _InterpolatorND:
+    """Shared machinery of Interpolator1D/2D/3D (_spline.py:48-441): tables live on the
+    device; slopes are precomputed once on the UN-padded tables (:380-393) and, for the
+    cubic family, interleaved into the AoS layout the evaluation kernel streams best."""
+
+    _ndim = 0
+
+    def _setup(self, knots, f, method, extrap, period, kwargs):
+        ndim = self._ndim
+        names = TABLES[ndim]
+        kwargs = dict(kwargs)
+        self.axis = kwargs.pop("axis", 0)
+        given = {n: kwargs.pop(n, None) for n in names[1:]}
+        methods = (METHODS_1D, METHODS_2D, METHODS_3D)[ndim - 1]
+        fshape = _shape(f)
+        _check_shapes(ndim, knots, fshape)
+        errorif(method not in methods, ValueError, f"unknown method {method}")
+        io = _Inputs(ndim, (), knots, f)
+        kn = [io.coords(k) for k in knots]
+        errorif(ndim == 1 and self.axis != 0, NotImplementedError, "only axis=0 is supported")
+        errorif(io.complex and method == "akima" and any(v is None for v in given.values()),
+                NotImplementedError, "akima slopes of complex data are not implemented")
+        self.method = method
+        self.extrap = extrap
+        self.period = period
+        self._io = io
+        self._fshape = fshape
+        self._knots = kn
+        tabs = {"f": io.table(f)}
+        for n in names[1:]:
+            tabs[n] = None if given[n] is None else io.table(given[n])
+        for name, src, ax in CHAIN[ndim]:
+            if tabs[name] is None:
+                tabs[name] = _slopes_dev(kn[ax], tabs[src], method, ax, kwargs)
+        self._tabs = tabs
+        self._batch = int(np.prod(tabs["f"].shape[ndim:], dtype=np.int64))
+        self._packed = None
+        if _method_class(method) == L.IPX_CUBIC:
+            self._packed = _pack_dev(ndim, [tabs[n] for n in names])
+        self._pk_cache = {}
+
+    # the reference exposes these as pytree leaves
+    @property
+    def f(self):
+        return self._user(self._tabs["f"])
+
+    @property
+    def derivs(self):
+        return {n: self._user(self._tabs[n]) for n in TABLES[self._ndim][1:]}
+
+    def _user(self, t):
+        if self._io.complex:
+            return torch.view_as_complex(t)
+        return t
+
+    def _periodic(self, ax, per):
+        key = (ax, abs(float(per)))
+        if key not in self._pk_cache:
+            self._pk_cache[key] = _periodic_knots_dev(self._knots[ax], per)
+        return self._pk_cache[key]
+
+    def _call(self, qs, derivative, return_index=False):
+        ndim = self._ndim
+        io = self._io
+        want_torch = any(isinstance(q, torch.Tensor) for q in qs) or io.want_torch
+        qdt = _promote([*qs, *[np.zeros((), io.xdt)]])
+        # promotion of the call mirrors interpNd(xq, self.x, self.f, ...)
+        call_io = _Inputs.__new__(_Inputs)
+        call_io.want_torch = want_torch
+        call_io.dev = io.dev
+        call_io.xdt = qdt
+        call_io.fdt = np.dtype(np.result_type(io.fdt, qdt))
+        call_io.complex = io.complex
+        call_io.rdt = np.dtype(np.float64) if call_io.fdt in (np.float64, np.complex128) else np.dtype(np.float32)
+        if call_io.rdt != io.rdt:
+            # queries wider than the stored tables: fall back to the functional form, which
+            # promotes everything exactly as the reference does
+            tabs = {n: self._user(self._tabs[n]) for n in TABLES[ndim][1:]}
+            res = _interp(ndim, qs, [k for k in self._knots], self._user(self._tabs["f"]),
+                          self.method, derivative, self.extrap, self.period, tabs, return_index)
+            if want_torch:
+                return res
+            to_np = lambda t: t.cpu().numpy() if isinstance(t, torch.Tensor) else t
+            return tuple(to_np(r) for r in res) if return_index else to_np(res)
+        qd = [call_io.coords(q) for q in qs]
+        qd = list(torch.broadcast_tensors(*qd)) if ndim > 1 else qd
+        outshape = tuple(qd[0].shape) + tuple(self._fshape[ndim:])
+        qd = [q.contiguous().reshape(-1) for q in qd]
+        periods = _parse_ndarg(self.period, ndim)
+        derivs = _parse_ndarg(derivative, ndim)
+        ex = _parse_extrap(self.extrap, ndim)
+        mask = 0
+        perms = [None] * ndim
+        kuse = list(self._knots)
+        for ax in range(ndim):
+            if periods[ax] is not None:
+                kuse[ax], perms[ax] = self._periodic(ax, periods[ax])
+                mask |= L.IPX_PERIODIC(ax)
+        mclass = _method_class(self.method)
+        if mclass == L.IPX_CUBIC:
+            tables, layout = [self._packed], L.IPX_AOS
+        else:
+            tables, layout = [self._tabs["f"]], L.IPX_SOA
+        ns = [self._tabs["f"].shape[ax] for ax in range(ndim)]
+        params = _make_params(ndim, derivs, ex, periods)
+        out, idx = _eval_dev(ndim, qd, kuse, perms, ns, tables, layout, self._batch, mclass, mask,
+                             params, return_index)
+        res = call_io.finish(out, outshape)
+        if return_index:
+            return res, (idx if want_torch else idx.cpu().numpy())
+        return res
+
+
+class Interpolator1D(_InterpolatorND):
+    """Convenience class for a 1D interpolated function; same contract as
+    interpax.Interpolator1D (_spline.py:48-150)."""
+
+    _ndim = 1
+
+    def __init__(self, x, f, method="cubic", extrap=False, period=None, **kwargs):
+        self._setup((x,), f, method, extrap, period, kwargs)
+
+    @property
+    def x(self):
+        return self._knots[0]
+
+    def __call__(self, xq, dx=0):
+        return self._call((xq,), (dx,))
+
+
+class Interpolator2D(_InterpolatorND):
+    """Same contract as interpax.Interpolator2D (_spline.py:153-278)."""
+
+    _ndim = 2
+
+    def __init__(self, x, y, f, method="cubic", extrap=False, period=None, **kwargs):
+        self._setup((x, y), f, method, extrap, period, kwargs)
+
+    @property
+    def x(self):
+        return self._knots[0]
+
+    @property
+    def y(self):
+        return self._knots[1]
+
+    def __call__(self, xq, yq, dx=0, dy=0):
+        return self._call((xq, yq), (dx, dy))
+
+
+class Interpolator3D(_InterpolatorND):
+    """Same contract as interpax.Interpolator3D (_spline.py:281-441)."""
+
+    _ndim = 3
+
+    def __init__(self, x, y, z, f, method="cubic", extrap=False, period=None, **kwargs):
+        self._setup((x, y, z), f, method, extrap, period, kwargs)
+
+    @property
+    def x(self):
+        return self._knots[0]
+
+    @property
+    def y(self):
+        return self._knots[1]
+
+    @property
+    def z(self):
+        return self._knots[2]
+
+    def __call__(self, xq, yq, zq, dx=0, dy=0, dz=0):
+        return self._call((xq, yq, zq), (dx, dy, dz))

@@ -1,0 +1,263 @@
+// ipx_device.cuh -- device-side building blocks shared by the evaluation kernels.
+//
+// Reference behaviour restated here (paths relative to the reference repo):
+//   bin lookup            interpax/_spline.py:571 (and the 8 other call sites)
+//   local coordinate      interpax/_spline.py:576-579
+//   monomial weights      interpax/_spline.py:1138-1151 (_get_t_der)
+//   Hermite basis         interpax/_coefs.py:158-163   (A_CUBIC)
+//   periodic wrap         interpax/_spline.py:1117-1122
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/ipx.h"
+
+namespace ipx {
+
+// ------------------------------------------------------------------------------------
+// small typed helpers
+// ------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ T t_abs(T v);
+template <> __device__ __forceinline__ float t_abs<float>(float v) { return fabsf(v); }
+template <> __device__ __forceinline__ double t_abs<double>(double v) { return fabs(v); }
+
+template <typename T> __device__ __forceinline__ T t_sqrt(T v);
+template <> __device__ __forceinline__ float t_sqrt<float>(float v) { return sqrtf(v); }
+template <> __device__ __forceinline__ double t_sqrt<double>(double v) { return sqrt(v); }
+
+template <typename T> __device__ __forceinline__ T t_fmod(T a, T b);
+template <> __device__ __forceinline__ float t_fmod<float>(float a, float b) { return fmodf(a, b); }
+template <> __device__ __forceinline__ double t_fmod<double>(double a, double b) { return fmod(a, b); }
+
+template <typename T> __device__ __forceinline__ int t_floor_to_int(T v);
+template <> __device__ __forceinline__ int t_floor_to_int<float>(float v) { return __float2int_rd(v); }
+template <> __device__ __forceinline__ int t_floor_to_int<double>(double v) { return __double2int_rd(v); }
+
+// unfused multiply / add, used where the reference's op order must not be contracted
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+
+template <typename T> __device__ __forceinline__ T quiet_nan();
+template <> __device__ __forceinline__ float quiet_nan<float>() { return __int_as_float(0x7fc00000); }
+template <> __device__ __forceinline__ double quiet_nan<double>() {
+  return __longlong_as_double(0x7ff8000000000000LL);
+}
+
+// Python / jnp.remainder for a positive modulus: result in [0, P] with the sign of P.
+template <typename T> __device__ __forceinline__ T py_mod(T q, T P) {
+  T r = t_fmod(q, P);
+  if (r != T(0) && r < T(0)) r += P;
+  return r;
+}
+
+// where(dx == 0, 0, 1 / dx)
+template <typename T> __device__ __forceinline__ T safe_recip(T dx) {
+  return dx == T(0) ? T(0) : T(1) / dx;
+}
+
+// ------------------------------------------------------------------------------------
+// interval lookup:  i = clip(#{k : x[k] <= q}, 1, n-1)   (searchsorted side="right")
+//
+// Guess-and-verify.  The guess assumes uniformly spaced knots (x0 and inv_h come from
+// the first/last knot); it is then *verified against the real knots*, stepping one cell
+// if it is off by one and falling back to a full binary search otherwise, so the result
+// is exact for any non-decreasing knot vector.  NaN queries count as larger than every
+// knot (XLA's total-order comparator in jnp.searchsorted), i.e. i = n-1.
+// On return lo = x[i-1], hi = x[i].
+// ------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ int upper_bound_clipped(const T* __restrict__ x, int n, T q) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (x[mid] <= q) lo = mid + 1; else hi = mid;
+  }
+  return min(max(lo, 1), n - 1);
+}
+
+template <typename T>
+__device__ __forceinline__ int bin_index(const T* __restrict__ x, int n, T q, T x_first, T inv_h,
+                                         T& lo, T& hi) {
+  int i;
+  if (q != q) {
+    i = n - 1;
+    lo = x[i - 1];
+    hi = x[i];
+    return i;
+  }
+  i = t_floor_to_int((q - x_first) * inv_h) + 1;  // saturating; NaN -> 0
+  i = min(max(i, 1), n - 1);
+  lo = x[i - 1];
+  hi = x[i];
+  if (q < lo) {
+    if (i > 1) {
+      --i;
+      hi = lo;
+      lo = x[i - 1];
+      if (q < lo && i > 1) {
+        i = upper_bound_clipped(x, i, q);  // answer is in [1, i-1]
+        lo = x[i - 1];
+        hi = x[i];
+      }
+    }
+  } else if (q >= hi) {
+    if (i < n - 1) {
+      ++i;
+      lo = hi;
+      hi = x[i];
+      if (q >= hi && i < n - 1) {
+        i = upper_bound_clipped(x, n, q);
+        lo = x[i - 1];
+        hi = x[i];
+      }
+    }
+  }
+  return i;
+}
+
+// ------------------------------------------------------------------------------------
+// one axis of one query, located
+// ------------------------------------------------------------------------------------
+template <typename T> struct AxisDesc {
+  const T* __restrict__ q;           // queries along this axis
+  const T* __restrict__ knots;       // nk knots (padded + sorted when periodic)
+  const int32_t* __restrict__ perm;  // NULL or sorted position -> table index
+  int32_t n;                         // table extent along the axis
+  int32_t nk;                        // n, or n + 2 on a periodic axis
+  int32_t periodic;                  // padded knot position -> table index through perm
+  int32_t wrap;                      // wrap the query with the Python remainder
+};
+
+template <typename T> struct AxisLoc {
+  T q, x0, x1;      // wrapped query, cell end points
+  int32_t i;        // interval index (upper knot), in knot coordinates
+  int32_t t0, t1;   // table indices of the lower / upper corner
+  bool below, above;  // q < knots[0], q > knots[nk-1]
+};
+
+// per-block constants of one axis, computed once (see stage_axis_consts)
+template <typename T> struct AxisConst {
+  T x_first, x_last, inv_h;
+};
+
+template <typename T>
+__device__ __forceinline__ void axis_consts(const AxisDesc<T>& A, AxisConst<T>& C) {
+  C.x_first = A.knots[0];
+  C.x_last = A.knots[A.nk - 1];
+  T span = C.x_last - C.x_first;
+  C.inv_h = span > T(0) ? T(A.nk - 1) / span : T(0);
+}
+
+template <typename T>
+__device__ __forceinline__ void locate(const AxisDesc<T>& A, const AxisConst<T>& C,
+                                       const ipx_axis_params& P, int64_t qi, AxisLoc<T>& L) {
+  T q = A.q[qi];
+  if (A.wrap) q = py_mod(q, T(fabs(P.period)));
+  L.q = q;
+  L.i = bin_index(A.knots, A.nk, q, C.x_first, C.inv_h, L.x0, L.x1);
+  L.below = q < C.x_first;
+  L.above = q > C.x_last;
+  if (A.periodic) {
+    // padded position p -> sorted position (p-1) mod n -> table index perm[.]
+    int s0 = L.i - 2;
+    if (s0 < 0) s0 += A.n;
+    int s1 = L.i - 1;
+    if (s1 >= A.n) s1 -= A.n;
+    L.t0 = A.perm ? A.perm[s0] : s0;
+    L.t1 = A.perm ? A.perm[s1] : s1;
+  } else {
+    L.t0 = L.i - 1;
+    L.t1 = L.i;
+  }
+}
+
+// table index of padded knot position p on a periodic axis (used by 1-D nearest)
+template <typename T> __device__ __forceinline__ int padded_to_table(const AxisDesc<T>& A, int p) {
+  if (!A.periodic) return p;
+  int s = p - 1;
+  if (s < 0) s += A.n;
+  if (s >= A.n) s -= A.n;
+  return A.perm ? A.perm[s] : s;
+}
+
+// ------------------------------------------------------------------------------------
+// cubic Hermite weights of one axis.
+//   tt = n-th derivative of [1, t, t^2, t^3] times dxi^n        (_get_t_der)
+//   w  = tt . A_CUBIC,  then the two slope weights carry the cell width dx
+//        (the reference scales the slope tables by dx before the contraction,
+//         _spline.py:583-584, 790-793, 1086-1091)
+// w[0], w[1]: value at lower / upper corner;  w[2], w[3]: slope at lower / upper corner.
+// ------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void hermite_weights(const AxisLoc<T>& L, int order, T w[4]) {
+  T dx = L.x1 - L.x0;
+  T dxi = safe_recip(dx);
+  T t = (L.q - L.x0) * dxi;
+  T tt0, tt1, tt2, tt3;
+  if (order <= 0) {
+    tt0 = T(1); tt1 = t; tt2 = t * t; tt3 = tt2 * t;
+  } else if (order == 1) {
+    tt0 = T(0); tt1 = dxi; tt2 = (T(2) * t) * dxi; tt3 = (T(3) * (t * t)) * dxi;
+  } else if (order == 2) {
+    T s = dxi * dxi;
+    tt0 = T(0); tt1 = T(0); tt2 = T(2) * s; tt3 = (T(6) * t) * s;
+  } else if (order == 3) {
+    tt0 = T(0); tt1 = T(0); tt2 = T(0); tt3 = T(6) * (dxi * dxi * dxi);
+  } else {
+    T z = dxi * T(0);
+    tt0 = z; tt1 = z; tt2 = z; tt3 = z;
+  }
+  // columns of A_CUBIC = [[1,0,0,0],[0,0,1,0],[-3,3,-2,-1],[2,-2,1,1]]
+  w[0] = tt0 - T(3) * tt2 + T(2) * tt3;
+  w[1] = T(3) * tt2 - T(2) * tt3;
+  w[2] = (tt1 - T(2) * tt2 + tt3) * dx;
+  w[3] = (tt3 - tt2) * dx;
+}
+
+// (bi/tri)linear weights of one axis (_spline.py:745-753, 1008-1020); the common factor
+// dxi is returned separately because the reference multiplies it in after the sum.
+template <typename T>
+__device__ __forceinline__ void linear_weights(const AxisLoc<T>& L, int order, T w[2], T& dxi) {
+  dxi = safe_recip(L.x1 - L.x0);
+  if (order <= 0) {
+    w[0] = L.x1 - L.q; w[1] = L.q - L.x0;
+  } else if (order == 1) {
+    w[0] = T(-1); w[1] = T(1);
+  } else {
+    w[0] = T(0); w[1] = T(0);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// global loads.  Tables are read-only for the lifetime of a call: use the non-coherent
+// path; 128-bit where the record layout allows it.
+// ------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }
+
+__device__ __forceinline__ void ldg_rec2(const double* p, double* r) {
+  double2 v = __ldg(reinterpret_cast<const double2*>(p));
+  r[0] = v.x; r[1] = v.y;
+}
+__device__ __forceinline__ void ldg_rec2(const float* p, float* r) {
+  float2 v = __ldg(reinterpret_cast<const float2*>(p));
+  r[0] = v.x; r[1] = v.y;
+}
+__device__ __forceinline__ void ldg_rec4(const double* p, double* r) {
+  ldg_rec2(p, r); ldg_rec2(p + 2, r + 2);
+}
+__device__ __forceinline__ void ldg_rec4(const float* p, float* r) {
+  float4 v = __ldg(reinterpret_cast<const float4*>(p));
+  r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+}
+__device__ __forceinline__ void ldg_rec8(const double* p, double* r) {
+  ldg_rec4(p, r); ldg_rec4(p + 4, r + 4);
+}
+__device__ __forceinline__ void ldg_rec8(const float* p, float* r) {
+  ldg_rec4(p, r); ldg_rec4(p + 4, r + 4);
+}
+
+}  // namespace ipx

@@ -1,0 +1,495 @@
+// ipx_slopes.cu -- knot-slope precompute: approx_df as CUDA kernels.
+//
+// Replaces interpax/_fd_derivs.py:9-443 of the reference.  A C-contiguous table is
+// viewed as (outer, n, inner) with the differentiated axis in the middle, so no
+// moveaxis copy is made.  Local stencils (cubic, cardinal, monotonic, akima) are one
+// thread per output element, coalesced along the fastest table dimension; cubic2 (a
+// tridiagonal solve along the axis) is one thread per column with the knot-only part of
+// the Thomas recurrence factored out and shared by all columns.
+#include <cuda_runtime.h>
+
+#include "ipx_device.cuh"
+
+namespace ipx {
+
+constexpr int kSlopeThreads = 256;
+
+template <typename T> struct SlopeArgs {
+  const T* __restrict__ x;
+  const T* __restrict__ f;
+  T* __restrict__ out;
+  int64_t outer, inner;
+  int32_t n;
+};
+
+template <typename T>
+__device__ __forceinline__ T secant(const SlopeArgs<T>& a, int64_t base, int k) {
+  // s_k = (f[k+1] - f[k]) * where(dx == 0, 0, 1/dx)
+  T df = a.f[base + (int64_t)(k + 1) * a.inner] - a.f[base + (int64_t)k * a.inner];
+  return safe_recip(a.x[k + 1] - a.x[k]) * df;
+}
+
+template <typename T> __device__ __forceinline__ T sign_of(T v) {
+  return v > T(0) ? T(1) : (v < T(0) ? T(-1) : (v == T(0) ? T(0) : v));  // NaN stays NaN
+}
+
+template <typename T> __device__ __forceinline__ T safediv(T a, T b) {
+  // _fd_derivs.py:427-443 with fill = 0, threshold = 0
+  bool m = t_abs(b) <= T(0);
+  return (m ? T(0) : a) / (m ? T(1) : b);
+}
+
+// decompose a flat element index of the (outer, n, inner) view
+template <typename T>
+__device__ __forceinline__ void split_index(const SlopeArgs<T>& a, int64_t e, int64_t& base, int& k) {
+  int64_t i = e % a.inner;
+  int64_t r = e / a.inner;
+  k = (int)(r % a.n);
+  int64_t o = r / a.n;
+  base = o * a.n * a.inner + i;  // address of element k = 0 of this column
+}
+
+// ------------------------------------------------------------------ cubic  (_cubic1)
+template <typename T> __global__ void slopes_cubic_kernel(const SlopeArgs<T> a) {
+  const int64_t total = a.outer * a.n * a.inner;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    int64_t base; int k;
+    split_index(a, e, base, k);
+    T v;
+    if (k == 0) v = secant(a, base, 0);
+    else if (k == a.n - 1) v = secant(a, base, a.n - 2);
+    else v = T(0.5) * (secant(a, base, k - 1) + secant(a, base, k));
+    a.out[e] = v;
+  }
+}
+
+// ------------------------------------------------------------------ cardinal (_cardinal)
+template <typename T> __global__ void slopes_cardinal_kernel(const SlopeArgs<T> a, T one_minus_c) {
+  const int64_t total = a.outer * a.n * a.inner;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    int64_t base; int k;
+    split_index(a, e, base, k);
+    int lo = k == 0 ? 0 : k - 1;
+    int hi = k == a.n - 1 ? a.n - 1 : k + 1;
+    T df = a.f[base + (int64_t)hi * a.inner] - a.f[base + (int64_t)lo * a.inner];
+    T v = (k == 0 || k == a.n - 1) ? df * safe_recip(a.x[hi] - a.x[lo])
+                                   : safe_recip(a.x[hi] - a.x[lo]) * df;
+    a.out[e] = one_minus_c * v;
+  }
+}
+
+// ------------------------------------------------------------------ monotonic (_monotonic)
+template <typename T>
+__device__ __forceinline__ T pchip_edge(T h0, T h1, T m0, T m1) {
+  // _fd_derivs.py:365-376
+  T d = ((T(2) * h0 + h1) * m0 - h0 * m1) / (h0 + h1);
+  bool mask = sign_of(d) != sign_of(m0);
+  bool mask2 = (sign_of(m0) != sign_of(m1)) && (t_abs(d) > T(3) * t_abs(m0));
+  bool mmm = (!mask) && mask2;
+  if (mask) d = T(0);
+  if (mmm) d = T(3) * m0;
+  return d;
+}
+
+template <typename T> __global__ void slopes_monotonic_kernel(const SlopeArgs<T> a, int zero_ends) {
+  const int64_t total = a.outer * a.n * a.inner;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int n = a.n;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    int64_t base; int k;
+    split_index(a, e, base, k);
+    T v;
+    if (k == 0 || k == n - 1) {
+      if (zero_ends) {
+        v = T(0);
+      } else {
+        // intervals 0,1 at the start; n-2,n-3 at the end; JAX clamps the second index
+        // when there is only one interval (n == 2)
+        int j0 = k == 0 ? 0 : n - 2;
+        int j1 = k == 0 ? min(1, n - 2) : max(n - 3, 0);
+        T hi0 = safe_recip(a.x[j0 + 1] - a.x[j0]);
+        T hi1 = safe_recip(a.x[j1 + 1] - a.x[j1]);
+        T m0 = hi0 * (a.f[base + (int64_t)(j0 + 1) * a.inner] - a.f[base + (int64_t)j0 * a.inner]);
+        T m1 = hi1 * (a.f[base + (int64_t)(j1 + 1) * a.inner] - a.f[base + (int64_t)j1 * a.inner]);
+        v = pchip_edge(T(1) / hi0, T(1) / hi1, m0, m1);  // hk = 1 / hki, _fd_derivs.py:378
+      }
+    } else {
+      T h0 = a.x[k] - a.x[k - 1];      // hk[k-1]
+      T h1 = a.x[k + 1] - a.x[k];      // hk[k]
+      T fm = a.f[base + (int64_t)(k - 1) * a.inner];
+      T f0 = a.f[base + (int64_t)k * a.inner];
+      T fp = a.f[base + (int64_t)(k + 1) * a.inner];
+      T m0 = safe_recip(h0) * (f0 - fm);
+      T m1 = safe_recip(h1) * (fp - f0);
+      bool cond = (sign_of(m1) != sign_of(m0)) || (m1 == T(0)) || (m0 == T(0));
+      T w1 = T(2) * h1 + h0;
+      T w2 = h1 + T(2) * h0;
+      T whmean = safediv(safediv(w1, m0) + safediv(w2, m1), w1 + w2);
+      v = cond ? T(0) : safediv(T(1), whmean);
+    }
+    a.out[e] = v;
+  }
+}
+
+// ------------------------------------------------------------------ akima (_akima)
+// m[j], j in [0, n+2]: extended secant array of _fd_derivs.py:397-409 (zero-initialised,
+// which matters only for n == 2).
+template <typename T>
+__device__ __forceinline__ T akima_secant(const SlopeArgs<T>& a, int64_t base, int k) {
+  T dx = a.x[k + 1] - a.x[k];
+  bool z = dx == T(0);
+  T dxi = z ? T(0) : T(1) / dx;
+  return (a.f[base + (int64_t)(k + 1) * a.inner] - a.f[base + (int64_t)k * a.inner]) * dxi;
+}
+
+template <typename T>
+__device__ __forceinline__ T akima_m(const SlopeArgs<T>& a, int64_t base, int j) {
+  const int n = a.n;
+  if (j >= 2 && j <= n) return akima_secant(a, base, j - 2);
+  if (n == 2) {
+    // only one true secant s0 = m[2]; the reference reads m[3] before it is written
+    T s0 = akima_secant(a, base, 0);
+    T m1 = T(2) * s0 - T(0);
+    if (j == 1) return m1;
+    if (j == 0) return T(2) * m1 - s0;
+    T m3 = T(2) * s0 - m1;        // m[-2] = 2 m[-3] - m[-4]
+    if (j == 3) return m3;
+    return T(2) * m3 - s0;        // m[-1] = 2 m[-2] - m[-3]
+  }
+  if (j < 2) {
+    T m2 = akima_secant(a, base, 0), m3 = akima_secant(a, base, 1);
+    T m1 = T(2) * m2 - m3;
+    return j == 1 ? m1 : T(2) * m1 - m2;
+  }
+  T mn = akima_secant(a, base, n - 2), mn1 = akima_secant(a, base, n - 3);  // m[n], m[n-1]
+  T mp1 = T(2) * mn - mn1;                                                  // m[n+1]
+  return j == n + 1 ? mp1 : T(2) * mp1 - mn;
+}
+
+__device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
+  atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+}
+__device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
+  atomicMax(reinterpret_cast<unsigned long long*>(addr),
+            (unsigned long long)__double_as_longlong(v));
+}
+
+template <typename T> __global__ void akima_init_kernel(T* gmax) { *gmax = T(0); }
+
+template <typename T>
+__global__ void akima_max_kernel(const SlopeArgs<T> a, T* __restrict__ gmax) {
+  const int64_t total = a.outer * a.n * a.inner;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  T local = T(0);
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    int64_t base; int k;
+    split_index(a, e, base, k);
+    T m1 = akima_m(a, base, k), m2 = akima_m(a, base, k + 1);
+    T m3 = akima_m(a, base, k + 2), m4 = akima_m(a, base, k + 3);
+    T f12 = t_abs(m4 - m3) + t_abs(m2 - m1);
+    if (f12 > local) local = f12;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    T o = __shfl_xor_sync(0xffffffffu, local, off);
+    if (o > local) local = o;
+  }
+  if ((threadIdx.x & 31) == 0 && local > T(0)) atomic_max_nonneg(gmax, local);
+}
+
+template <typename T>
+__global__ void slopes_akima_kernel(const SlopeArgs<T> a, const T* __restrict__ gmax) {
+  const int64_t total = a.outer * a.n * a.inner;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const T thresh = T(1e-9) * (*gmax);
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    int64_t base; int k;
+    split_index(a, e, base, k);
+    T m1 = akima_m(a, base, k), m2 = akima_m(a, base, k + 1);
+    T m3 = akima_m(a, base, k + 2), m4 = akima_m(a, base, k + 3);
+    T m4m3 = t_abs(m4 - m3), m2m1 = t_abs(m2 - m1);
+    T f12 = m4m3 + m2m1;
+    bool mask = f12 > thresh;
+    T df = (m4m3 * m2 + m2m1 * m3) / (mask ? f12 : T(1));
+    a.out[e] = mask ? df : T(0.5) * (m4 + m1);  // the code's 0.5*(m[3:]+m[:-3]), _fd_derivs.py:423
+  }
+}
+
+// ------------------------------------------------------------------ cubic2 (_cubic2)
+template <typename T> struct BcArgs {
+  int32_t start, end;                       // IPX_BC_*
+  const T* __restrict__ start_value;        // per column or NULL (zeros)
+  const T* __restrict__ end_value;
+};
+
+// row k of the tridiagonal system: sub-diagonal a_k (A[k,k-1]), diagonal b_k, super-diagonal
+// c_k (A[k,k+1]) -- knots and boundary kinds only (_fd_derivs.py:208-213, 219-222, 231-239,
+// 250-253, 262-270), then the duplicate-knot neutralisation (:281-285).
+template <typename T>
+__device__ __forceinline__ void cubic2_row(const T* __restrict__ x, int n, int bs, int be, int k,
+                                           T& lower, T& diag, T& upper, bool& masked) {
+  lower = T(0); upper = T(0);
+  if (k == 0) {
+    if (bs == IPX_BC_NOT_A_KNOT) { diag = x[2] - x[1]; upper = x[2] - x[0]; }
+    else if (bs == IPX_BC_FIRST) { diag = T(1); upper = T(0); }
+    else { T d0 = x[1] - x[0]; diag = T(2) * d0; upper = d0; }
+  } else if (k == n - 1) {
+    if (be == IPX_BC_NOT_A_KNOT) { diag = x[n - 2] - x[n - 3]; lower = x[n - 1] - x[n - 3]; }
+    else if (be == IPX_BC_FIRST) { diag = T(1); lower = T(0); }
+    else { T d1 = x[n - 1] - x[n - 2]; diag = T(2) * d1; lower = d1; }
+  } else {
+    T dl = x[k] - x[k - 1], dr = x[k + 1] - x[k];
+    diag = T(2) * (dl + dr); upper = dl; lower = dr;
+  }
+  masked = diag == T(0);
+  if (masked) { diag = T(1); lower = T(0); upper = T(0); }
+}
+
+// knot-only part of the Thomas recurrence (lineax Tridiagonal solver order):
+//   den_k = b_k - a_k c'_{k-1};  c'_k = c_k / den_k
+// one thread, sequential; ws[0..n) = c', ws[n..2n) = den
+template <typename T>
+__global__ void cubic2_factor_kernel(const T* __restrict__ x, int n, int bs, int be,
+                                     T* __restrict__ ws) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  T cprev = T(0);
+  for (int k = 0; k < n; ++k) {
+    T lo, di, up;
+    bool masked;
+    cubic2_row(x, n, bs, be, k, lo, di, up, masked);
+    T den = di - lo * cprev;
+    cprev = up / den;
+    ws[k] = cprev;
+    ws[n + k] = den;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ T cubic2_rhs(const SlopeArgs<T>& a, const BcArgs<T>& bc, int64_t base,
+                                        int64_t col, int k, bool masked) {
+  const int n = a.n;
+  const T* __restrict__ x = a.x;
+  auto F = [&](int j) { return a.f[base + (int64_t)j * a.inner]; };
+  auto dxr = [&](int j) { return x[j + 1] - x[j]; };
+  auto s = [&](int j) {  // secant slope, with the reference's double `where` guard
+    T d = dxr(j);
+    T dxi = d == T(0) ? T(0) : T(1) / d;
+    return dxi * (F(j + 1) - F(j));
+  };
+  if (masked) return T(0);  // _fd_derivs.py:286
+  if (k == 0) {
+    if (bc.start == IPX_BC_NOT_A_KNOT) {
+      T d = x[2] - x[0];
+      return ((dxr(0) + T(2) * d) * dxr(1) * s(0) + dxr(0) * dxr(0) * s(1)) / d;
+    }
+    T v = bc.start_value ? bc.start_value[col] : T(0);
+    if (bc.start == IPX_BC_FIRST) return v;
+    T d0 = dxr(0);
+    return T(-0.5) * v * (d0 * d0) + T(3) * (F(1) - F(0));
+  }
+  if (k == n - 1) {
+    if (bc.end == IPX_BC_NOT_A_KNOT) {
+      T d = x[n - 1] - x[n - 3];
+      return (dxr(n - 2) * dxr(n - 2) * s(n - 3) + (T(2) * d + dxr(n - 2)) * dxr(n - 3) * s(n - 2)) / d;
+    }
+    T v = bc.end_value ? bc.end_value[col] : T(0);
+    if (bc.end == IPX_BC_FIRST) return v;
+    T d1 = dxr(n - 2);
+    return T(0.5) * v * (d1 * d1) + T(3) * (F(n - 1) - F(n - 2));
+  }
+  return T(3) * (dxr(k) * s(k - 1) + dxr(k - 1) * s(k));
+}
+
+// one thread per column: forward sweep d'_k = (d_k - a_k d'_{k-1}) / den_k into `out`,
+// then back substitution x_k = d'_k - c'_k x_{k+1} in place.
+template <typename T>
+__global__ void cubic2_solve_kernel(const SlopeArgs<T> a, const BcArgs<T> bc,
+                                    const T* __restrict__ ws) {
+  const int64_t cols = a.outer * a.inner;
+  const int n = a.n;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; col < cols; col += stride) {
+    int64_t o = col / a.inner, i = col - o * a.inner;
+    int64_t base = o * n * a.inner + i;
+    T dprev = T(0);
+    for (int k = 0; k < n; ++k) {
+      T lo, di, up;
+      bool masked;
+      cubic2_row(a.x, n, bc.start, bc.end, k, lo, di, up, masked);
+      T rhs = cubic2_rhs(a, bc, base, col, k, masked);
+      dprev = (rhs - lo * dprev) / ws[n + k];
+      a.out[base + (int64_t)k * a.inner] = dprev;
+    }
+    T xnext = T(0);
+    for (int k = n - 1; k >= 0; --k) {
+      xnext = a.out[base + (int64_t)k * a.inner] - ws[k] * xnext;
+      a.out[base + (int64_t)k * a.inner] = xnext;
+    }
+  }
+}
+
+// n == 2: both ends take the secant when not-a-knot (_fd_derivs.py:175-179), then the
+// 2x2 system is solved by the same recurrence.  n == 3 with two not-a-knots: the parabola
+// through the three points, a dense 3x3 solve with partial pivoting (:185-203).
+template <typename T>
+__global__ void cubic2_small_kernel(const SlopeArgs<T> a, const BcArgs<T> bc) {
+  const int64_t cols = a.outer * a.inner;
+  const int n = a.n;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const T* __restrict__ x = a.x;
+  for (int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; col < cols; col += stride) {
+    int64_t o = col / a.inner, i = col - o * a.inner;
+    int64_t base = o * n * a.inner + i;
+    auto F = [&](int j) { return a.f[base + (int64_t)j * a.inner]; };
+    if (n == 2) {
+      T dx0 = x[1] - x[0];
+      T s0 = (dx0 == T(0) ? T(0) : T(1) / dx0) * (F(1) - F(0));
+      // rows: start row (diag, upper, rhs), end row (lower, diag, rhs)
+      T d0, u0, r0, l1, d1, r1;
+      if (bc.start == IPX_BC_NOT_A_KNOT) { d0 = T(1); u0 = T(0); r0 = s0; }
+      else if (bc.start == IPX_BC_FIRST) { d0 = T(1); u0 = T(0); r0 = bc.start_value ? bc.start_value[col] : T(0); }
+      else { d0 = T(2) * dx0; u0 = dx0; r0 = T(-0.5) * (bc.start_value ? bc.start_value[col] : T(0)) * (dx0 * dx0) + T(3) * (F(1) - F(0)); }
+      if (bc.end == IPX_BC_NOT_A_KNOT) { d1 = T(1); l1 = T(0); r1 = s0; }
+      else if (bc.end == IPX_BC_FIRST) { d1 = T(1); l1 = T(0); r1 = bc.end_value ? bc.end_value[col] : T(0); }
+      else { d1 = T(2) * dx0; l1 = dx0; r1 = T(0.5) * (bc.end_value ? bc.end_value[col] : T(0)) * (dx0 * dx0) + T(3) * (F(1) - F(0)); }
+      if (d0 == T(0)) { d0 = T(1); u0 = T(0); r0 = T(0); }
+      if (d1 == T(0)) { d1 = T(1); l1 = T(0); r1 = T(0); }
+      T den0 = d0;
+      T dp0 = r0 / den0, cp0 = u0 / den0;
+      T den1 = d1 - l1 * cp0;
+      T dp1 = (r1 - l1 * dp0) / den1;
+      a.out[base + a.inner] = dp1;
+      a.out[base] = dp0 - cp0 * dp1;
+    } else {  // n == 3, not-a-knot at both ends
+      T dx0 = x[1] - x[0], dx1 = x[2] - x[1];
+      T s0 = (dx0 == T(0) ? T(0) : T(1) / dx0) * (F(1) - F(0));
+      T s1 = (dx1 == T(0) ? T(0) : T(1) / dx1) * (F(2) - F(1));
+      T A[3][4] = {{T(1), T(1), T(0), T(2) * s0},
+                   {dx1, T(2) * (dx0 + dx1), dx0, T(3) * (dx0 * s1 + dx1 * s0)},
+                   {T(0), T(1), T(1), T(2) * s1}};
+      // LU with partial pivoting (what jnp.linalg.solve does)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        int piv = c;
+#pragma unroll
+        for (int r = c + 1; r < 3; ++r)
+          if (t_abs(A[r][c]) > t_abs(A[piv][c])) piv = r;
+        if (piv != c) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { T t = A[c][j]; A[c][j] = A[piv][j]; A[piv][j] = t; }
+        }
+#pragma unroll
+        for (int r = c + 1; r < 3; ++r) {
+          T m = A[r][c] / A[c][c];
+#pragma unroll
+          for (int j = c; j < 4; ++j) A[r][j] -= m * A[c][j];
+        }
+      }
+      T v2 = A[2][3] / A[2][2];
+      T v1 = (A[1][3] - A[1][2] * v2) / A[1][1];
+      T v0 = (A[0][3] - A[0][1] * v1 - A[0][2] * v2) / A[0][0];
+      a.out[base] = v0;
+      a.out[base + a.inner] = v1;
+      a.out[base + 2 * a.inner] = v2;
+    }
+  }
+}
+
+template <typename T> __global__ void fill_zero_kernel(T* __restrict__ out, int64_t total) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride)
+    out[e] = T(0);
+}
+
+static int slope_grid(int64_t total) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess)
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t need = (total + kSlopeThreads - 1) / kSlopeThreads;
+  int64_t cap = (int64_t)sms * 16;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+template <typename T>
+static int launch_slopes(const T* x, int32_t n, const T* f, int64_t outer, int64_t inner,
+                         int32_t method, const ipx_slope_opts* opts, T* out, void* workspace,
+                         void* stream) {
+  if (outer < 0 || inner < 0 || n < 0) return IPX_EINVAL;
+  const int64_t total = outer * n * inner;
+  if (total == 0) return IPX_OK;
+  if (x == nullptr || f == nullptr || out == nullptr) return IPX_EINVAL;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  SlopeArgs<T> a{x, f, out, outer, inner, n};
+  const int grid = slope_grid(total);
+  switch (method) {
+    case IPX_SLOPE_ZERO:
+      fill_zero_kernel<T><<<grid, kSlopeThreads, 0, s>>>(out, total);
+      break;
+    case IPX_SLOPE_CUBIC:
+      if (n < 2) return IPX_EINVAL;
+      slopes_cubic_kernel<T><<<grid, kSlopeThreads, 0, s>>>(a);
+      break;
+    case IPX_SLOPE_CARDINAL: {
+      if (n < 2) return IPX_EINVAL;
+      T c = opts ? T(opts->c) : T(0);
+      slopes_cardinal_kernel<T><<<grid, kSlopeThreads, 0, s>>>(a, T(1) - c);
+      break;
+    }
+    case IPX_SLOPE_MONOTONIC:
+    case IPX_SLOPE_MONOTONIC0:
+      if (n < 2) return IPX_EINVAL;
+      slopes_monotonic_kernel<T><<<grid, kSlopeThreads, 0, s>>>(a, method == IPX_SLOPE_MONOTONIC0);
+      break;
+    case IPX_SLOPE_AKIMA: {
+      if (n < 2 || workspace == nullptr) return IPX_EINVAL;
+      T* gmax = static_cast<T*>(workspace);
+      akima_init_kernel<T><<<1, 1, 0, s>>>(gmax);
+      akima_max_kernel<T><<<grid, kSlopeThreads, 0, s>>>(a, gmax);
+      slopes_akima_kernel<T><<<grid, kSlopeThreads, 0, s>>>(a, gmax);
+      break;
+    }
+    case IPX_SLOPE_CUBIC2: {
+      if (n < 2) return IPX_EINVAL;
+      BcArgs<T> bc;
+      bc.start = opts ? opts->bc_start : IPX_BC_NOT_A_KNOT;
+      bc.end = opts ? opts->bc_end : IPX_BC_NOT_A_KNOT;
+      bc.start_value = opts ? static_cast<const T*>(opts->bc_start_value) : nullptr;
+      bc.end_value = opts ? static_cast<const T*>(opts->bc_end_value) : nullptr;
+      if (bc.start < 0 || bc.start > 2 || bc.end < 0 || bc.end > 2) return IPX_EINVAL;
+      const int cgrid = slope_grid(outer * inner);
+      if (n == 2 || (n == 3 && bc.start == IPX_BC_NOT_A_KNOT && bc.end == IPX_BC_NOT_A_KNOT)) {
+        cubic2_small_kernel<T><<<cgrid, kSlopeThreads, 0, s>>>(a, bc);
+      } else {
+        if (workspace == nullptr) return IPX_EINVAL;
+        T* ws = static_cast<T*>(workspace);
+        cubic2_factor_kernel<T><<<1, 32, 0, s>>>(x, n, bc.start, bc.end, ws);
+        cubic2_solve_kernel<T><<<cgrid, kSlopeThreads, 0, s>>>(a, bc, ws);
+      }
+      break;
+    }
+    default:
+      return IPX_EINVAL;
+  }
+  return cudaPeekAtLastError() == cudaSuccess ? IPX_OK : IPX_ELAUNCH;
+}
+
+}  // namespace ipx
+
+extern "C" size_t ipx_slopes_workspace_bytes(int32_t method, int32_t n, int32_t elem_size) {
+  if (method == IPX_SLOPE_AKIMA) return 16;
+  if (method == IPX_SLOPE_CUBIC2) return (size_t)2 * (size_t)(n > 0 ? n : 0) * (size_t)elem_size + 16;
+  return 0;
+}
+extern "C" int ipx_slopes_f32(const float* x, int32_t n, const float* f, int64_t outer,
+                              int64_t inner, int32_t method, const ipx_slope_opts* opts,
+                              float* out, void* workspace, void* stream) {
+  return ipx::launch_slopes<float>(x, n, f, outer, inner, method, opts, out, workspace, stream);
+}
+extern "C" int ipx_slopes_f64(const double* x, int32_t n, const double* f, int64_t outer,
+                              int64_t inner, int32_t method, const ipx_slope_opts* opts,
+                              double* out, void* workspace, void* stream) {
+  return ipx::launch_slopes<double>(x, n, f, outer, inner, method, opts, out, workspace, stream);
+}

@@ -1,0 +1,564 @@
+"""GPU parity tests: the CUDA path (through the public API -> C ABI -> libipx.so) against the
+CPU oracle (oracle/interpax_np.py) on the same seeded inputs.
+
+Bars (BASELINE.json north_star):
+  * interval indices: bit-exact against searchsorted(side="right") + clip;
+  * values and derivatives: rtol 1e-12 in float64, 1e-5 in float32, each paired with
+    atol = rtol * max|oracle result| (the reference's tests always pair rtol with an atol;
+    a pure rtol is meaningless at zero crossings of the interpolant).
+"""
+
+import ctypes as C
+import itertools
+
+import numpy as np
+import pytest
+import torch
+
+import interpax_b200 as ipx
+from interpax_b200 import _lib as L
+from interpax_b200 import api
+from oracle import interpax_np as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = {np.dtype(np.float64): 1e-12, np.dtype(np.float32): 1e-5,
+        np.dtype(np.complex128): 1e-12, np.dtype(np.complex64): 1e-5}
+ALL_METHODS = O.METHODS
+
+
+def assert_parity(got, want, what=""):
+    got = np.asarray(got)
+    want = np.asarray(want)
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    assert got.dtype == want.dtype, (what, got.dtype, want.dtype)
+    rtol = RTOL[np.dtype(want.dtype)]
+    fin = np.isfinite(want)
+    assert np.array_equal(np.isnan(got), np.isnan(want)), what
+    assert np.array_equal(np.isinf(got), np.isinf(want)), what
+    if fin.any():
+        scale = np.abs(want[fin]).max()
+        np.testing.assert_allclose(got[fin], want[fin], rtol=rtol, atol=rtol * scale, err_msg=what)
+
+
+def knots_nonuniform(rng, n, lo, hi, dtype):
+    x = np.sort(rng.uniform(lo, hi, n))
+    x[0], x[-1] = lo, hi
+    return x.astype(dtype)
+
+
+# ------------------------------------------------------------------ C1: the README example
+def test_readme_example_c1():
+    xp = np.linspace(0, 2 * np.pi, 100)
+    xq = np.linspace(0, 2 * np.pi, 10000)
+    fp = np.sin(xp)
+    fq, idx = api._interp(1, (xq,), (xp,), fp, "cubic", 0, False, None, {}, return_index=True)
+    np.testing.assert_allclose(fq, np.sin(xq), rtol=1e-6, atol=1e-5)  # README.rst:32-44
+    assert_parity(fq, O.interp1d(xq, xp, fp, method="cubic"))
+    assert np.array_equal(idx[0], O.bin_index(xp, xq).astype(np.int32))
+
+
+# ------------------------------------------------------------------ interval indices, bit-exact
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_bin_index_bit_exact(dtype):
+    rng = np.random.default_rng(1)
+    cases = []
+    cases.append(np.linspace(0, 1, 1000).astype(dtype))                      # uniform
+    cases.append(knots_nonuniform(rng, 777, -3, 5, dtype))                   # non-uniform
+    x = knots_nonuniform(rng, 300, 0, 1, dtype)
+    x[50:60] = x[50]                                                         # duplicated knots
+    x[-3:] = x[-1]
+    cases.append(x)
+    cases.append(np.array([0.0, 1.0], dtype=dtype))                          # two knots
+    cases.append(np.concatenate([np.linspace(0, 1e-3, 500), np.linspace(1, 100, 500)]).astype(dtype))
+    cases.append(np.zeros(16, dtype=dtype))                                  # all equal
+    for x in cases:
+        span = float(x[-1] - x[0]) or 1.0
+        q = rng.uniform(x[0] - 0.1 * span, x[-1] + 0.1 * span, 20000).astype(dtype)
+        special = np.array([np.nan, np.inf, -np.inf, 0.0, -0.0, x[0], x[-1], np.nextafter(x[0], -np.inf),
+                            np.nextafter(x[-1], np.inf)], dtype=dtype)
+        q = np.concatenate([q, special, x, np.nextafter(x, dtype(np.inf)), np.nextafter(x, dtype(-np.inf))])
+        got = ipx.bin_index(x, q)
+        assert got.dtype == np.int32
+        assert np.array_equal(got, O.bin_index(x, q)), len(x)
+
+
+def test_bin_index_million_knots():
+    rng = np.random.default_rng(2)
+    x = np.linspace(0, 1, 1_000_000)
+    xj = np.sort(x + 0.3 * (x[1] - x[0]) * rng.uniform(-1, 1, x.size))      # C2's jittered variant
+    q = rng.uniform(-0.01, 1.01, 1 << 20)
+    for knots in (x, xj):
+        assert np.array_equal(ipx.bin_index(knots, q), O.bin_index(knots, q))
+
+
+# ------------------------------------------------------------------ slope stencils
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("method", list(O.CUBIC_METHODS) + ["linear"])
+def test_slopes_vs_oracle(method, dtype):
+    rng = np.random.default_rng(3)
+    for shape, axis in [((40,), 0), ((33, 5), 0), ((4, 29), 1), ((3, 17, 6), 1), ((5, 4, 21), 2),
+                        ((2,), 0), ((3,), 0), ((4,), 0), ((2, 3), 0), ((3, 2), 0)]:
+        n = shape[axis]
+        x = knots_nonuniform(rng, n, 0, 2, dtype)
+        f = rng.normal(size=shape).astype(dtype)
+        kw = {"c": 0.3} if method == "cardinal" else {}
+        want = O.approx_df(x, f, method, axis, **kw)
+        got = ipx.approx_df(x, f, method, axis, **kw)
+        assert_parity(got, want.astype(dtype), f"{method} {shape} axis={axis}")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_slopes_duplicate_knots_and_flat_data(dtype):
+    rng = np.random.default_rng(4)
+    x = knots_nonuniform(rng, 30, 0, 1, dtype)
+    x[10] = x[11]
+    x[20:23] = x[20]
+    f = rng.normal(size=(30, 3)).astype(dtype)
+    f[5:9] = f[5]  # flat stretch: monotonic zero slopes, akima degenerate weights
+    for method in O.CUBIC_METHODS:
+        if method == "cubic2":
+            continue  # a duplicated knot makes the reference's system singular up to rounding
+        assert_parity(ipx.approx_df(x, f, method, 0), O.approx_df(x, f, method, 0).astype(dtype), method)
+    z = np.zeros((12, 2), dtype=dtype)
+    xx = np.arange(12).astype(dtype)
+    for method in O.CUBIC_METHODS:
+        assert_parity(ipx.approx_df(xx, z, method, 0), O.approx_df(xx, z, method, 0).astype(dtype), method)
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 25])
+def test_cubic2_boundary_conditions(n):
+    rng = np.random.default_rng(5)
+    x = knots_nonuniform(rng, n, 0, 3, np.float64)
+    f = rng.normal(size=(n, 2, 3))
+    v1 = rng.normal(size=(2, 3))
+    v2 = rng.normal(size=(2, 3))
+    kinds = ["not-a-knot", "natural", "clamped", (1, v1), (2, v2)]
+    for bs, be in itertools.product(kinds, kinds):
+        want = O.approx_df(x, f, "cubic2", 0, bc_type=(bs, be))
+        got = ipx.approx_df(x, f, "cubic2", 0, bc_type=(bs, be))
+        assert_parity(got, want, f"n={n} {bs if isinstance(bs, str) else bs[0]} {be if isinstance(be, str) else be[0]}")
+
+
+# ------------------------------------------------------------------ periodic knot preparation
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_periodic_knots_vs_oracle(dtype):
+    rng = np.random.default_rng(6)
+    P = 2 * np.pi
+    cases = [
+        np.linspace(0, P, 64, endpoint=False),          # sorted inside the period
+        np.linspace(0, P, 200),                         # inclusive end: 2pi % 2pi == 0 -> tie across the wrap
+        np.linspace(1.0, 1.0 + P, 50, endpoint=False),  # rotation
+        np.linspace(-3.0, -3.0 + P, 81),                # rotation with a tie
+        np.sort(rng.uniform(-20, 20, 97)),              # several periods: generic stable sort
+        np.array([0.5, 0.5, 0.5, 7.0]),
+    ]
+    for x in cases:
+        x = x.astype(dtype)
+        xt = torch.from_numpy(x).cuda()
+        xpad, perm = api._periodic_knots_dev(xt, P)
+        _, want_x, want_p = O._make_periodic(np.zeros(1, dtype), x, P, 0, np.arange(len(x)))
+        assert np.array_equal(xpad.cpu().numpy(), want_x)
+        # the oracle's padded index vector is [perm[-1], perm..., perm[0]]
+        assert np.array_equal(perm.cpu().numpy(), want_p[1:-1])
+
+
+# ------------------------------------------------------------------ evaluation: randomised sweep
+def make_problem(rng, ndim, dtype, batch_shape, uniform):
+    ns = [int(rng.integers(5, 14)) for _ in range(ndim)]
+    los = [float(rng.uniform(-2, 0)) for _ in range(ndim)]
+    his = [lo + float(rng.uniform(1, 4)) for lo in los]
+    if uniform:
+        knots = [np.linspace(lo, hi, n).astype(dtype) for lo, hi, n in zip(los, his, ns)]
+    else:
+        knots = [knots_nonuniform(rng, n, lo, hi, dtype) for lo, hi, n in zip(los, his, ns)]
+    f = rng.normal(size=(*ns, *batch_shape)).astype(dtype)
+    nq = 513
+    qs = []
+    for lo, hi in zip(los, his):
+        span = hi - lo
+        q = rng.uniform(lo - 0.25 * span, hi + 0.25 * span, nq)
+        q[:4] = [lo, hi, lo - 0.1, hi + 0.1]
+        qs.append(q.astype(dtype))
+    return knots, f, qs, los, his
+
+
+EXTRAPS = {
+    1: [False, True, 0.5, (True, False), (-1.0, True)],
+    2: [False, True, 2.5, (False, True), ((True, 1.5), (False, True))],
+    3: [False, True, -0.25, (3.0, False), ((True, True), (False, 2.0), (7.0, True))],
+}
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("method", ALL_METHODS)
+@pytest.mark.parametrize("ndim", [1, 2, 3])
+def test_eval_sweep_vs_oracle(ndim, method, dtype):
+    rng = np.random.default_rng(100 * ndim + len(method))
+    ofun = (O.interp1d, O.interp2d, O.interp3d)[ndim - 1]
+    gfun = (ipx.interp1d, ipx.interp2d, ipx.interp3d)[ndim - 1]
+    ocls = (O.Interpolator1D, O.Interpolator2D, O.Interpolator3D)[ndim - 1]
+    gcls = (ipx.Interpolator1D, ipx.Interpolator2D, ipx.Interpolator3D)[ndim - 1]
+    trial = 0
+    for batch_shape in [(), (3,), (2, 2)]:
+        for uniform in (True, False):
+            knots, f, qs, los, his = make_problem(rng, ndim, dtype, batch_shape, uniform)
+            for extrap in EXTRAPS[ndim]:
+                trial += 1
+                if ndim == 1:
+                    deriv = int(rng.integers(0, 5))
+                    dcall = (deriv,)
+                else:
+                    deriv = tuple(int(v) for v in rng.integers(0, 4, ndim))
+                    if trial % 3 == 0:
+                        deriv = 0
+                    dcall = (deriv,) * ndim if np.isscalar(deriv) else deriv
+                if trial % 4 == 1:
+                    per_axes = [bool(rng.integers(0, 2)) for _ in range(ndim)]
+                    if not any(per_axes):
+                        per_axes[0] = True
+                    period = tuple((hi - lo) * 1.07 if p else None for lo, hi, p in zip(los, his, per_axes))
+                    if ndim == 1:
+                        period = period[0]
+                else:
+                    period = None
+                kw = {"c": 0.25} if method == "cardinal" else {}
+                what = f"nd={ndim} {method} B={batch_shape} uni={uniform} ex={extrap} d={deriv} per={period}"
+                want = ofun(*qs, *knots, f, method, deriv, extrap, period, **kw)
+                got = gfun(*qs, *knots, f, method, deriv, extrap, period, **kw)
+                assert_parity(got, want, "functional " + what)
+                want_c = ocls(*knots, f, method, extrap, period, **kw)(*qs, *dcall)
+                got_c = gcls(*knots, f, method, extrap, period, **kw)(*qs, *dcall)
+                assert_parity(got_c, want_c, "class " + what)
+
+
+@pytest.mark.parametrize("ndim", [1, 2, 3])
+def test_eval_indices_and_layouts(ndim):
+    """Indices from the fused kernel are bit-exact, and the AoS (packed) and SoA table
+    layouts give bit-identical values (same arithmetic, different loads)."""
+    rng = np.random.default_rng(40 + ndim)
+    knots, f, qs, los, his = make_problem(rng, ndim, np.float64, (2,), False)
+    for q, k in zip(qs, knots):
+        q[10] = np.nan
+        q[11:11 + len(k)] = k[: len(q) - 11][: len(k)]
+    res, idx = api._interp(ndim, qs, knots, f, "cubic", 0, True, None, {}, return_index=True)
+    for ax in range(ndim):
+        assert np.array_equal(idx[ax], O.bin_index(knots[ax], qs[ax]))
+    cls = (ipx.Interpolator1D, ipx.Interpolator2D, ipx.Interpolator3D)[ndim - 1]
+    got = cls(*knots, f, "cubic", True)(*qs)
+    assert np.array_equal(np.isnan(got), np.isnan(res))
+    m = ~np.isnan(res)
+    assert np.array_equal(got[m], res[m])
+
+
+def test_nearest_1d_ties_and_far_queries():
+    x = np.array([0.0, 1.0, 1.0, 2.0, 4.0])
+    f = np.array([10.0, 11.0, 12.0, 13.0, 14.0])
+    q = np.array([0.5, 1.0, 1.5, 3.0, -5.0, 9.0, 1e300, -1e300, np.nan, 2.0, 0.0])
+    want = O.interp1d(q, x, f, "nearest", 0, True)
+    got = ipx.interp1d(q, x, f, "nearest", 0, True)
+    assert np.array_equal(got, want)
+    xf = x.astype(np.float32)
+    qf = np.array([0.5, 1e30, -1e30, 3.0000001, 1.0], dtype=np.float32)
+    assert np.array_equal(ipx.interp1d(qf, xf, f.astype(np.float32), "nearest", 0, True),
+                          O.interp1d(qf, xf, f.astype(np.float32), "nearest", 0, True))
+
+
+# ------------------------------------------------------------------ the reference's own tests, restated
+TOL_1D = {
+    "nearest": (1e-2, 1e-1), "linear": (1e-4, 1e-3), "cubic": (1e-6, 1e-5), "cubic2": (1e-6, 1e-5),
+    "cardinal": (1e-6, 1e-5), "catmull-rom": (1e-6, 1e-5), "monotonic": (1e-4, 1e-3),
+    "monotonic-0": (1e-4, 1.5e-2), "akima": (1e-6, 2e-5),
+}
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex64, np.complex128])
+@pytest.mark.parametrize("scalar", [False, True])
+def test_reference_test_interp1d(dtype, scalar):
+    # tests/test_interpolate.py:26-82
+    xp = np.real(np.linspace(0, 2 * np.pi, 100).astype(dtype))
+    cplx = np.iscomplexobj(np.zeros(1, dtype))
+    f = (lambda x: np.sin(x) + 1j * np.sin(x)) if cplx else (lambda x: np.sin(x))
+    fp = f(xp).astype(dtype)
+    x = 0.0 if scalar else np.real(np.linspace(0, 2 * np.pi, 10000).astype(dtype))
+    for interp in (ipx.interp1d, lambda xq, *a, **k: ipx.Interpolator1D(*a, **k)(xq)):
+        for m, (rtol, atol) in TOL_1D.items():
+            if cplx and m == "akima":
+                with pytest.raises(NotImplementedError):
+                    interp(x, xp, fp, method=m)
+                continue
+            fq = interp(x, xp, fp, method=m)
+            assert fq.dtype == np.result_type(x, xp, fp), m
+            np.testing.assert_allclose(fq, f(x), rtol=rtol, atol=atol, err_msg=m)
+            assert_parity(fq, O.interp1d(x, xp, fp, method=m), m)
+
+
+def test_reference_test_interp1d_extrap_periodic_monotonic():
+    # tests/test_interpolate.py:117-149
+    xp = np.linspace(0, 2 * np.pi, 200)
+    x = np.linspace(-1, 2 * np.pi + 1, 10000)
+    fp = np.sin(xp)
+    fq = ipx.interp1d(x, xp, fp, method="cubic", extrap=False)
+    assert np.isnan(fq[0]) and np.isnan(fq[-1])
+    fq = ipx.interp1d(x, xp, fp, method="cubic", extrap=True)
+    assert not np.isnan(fq[0]) and not np.isnan(fq[-1])
+    fq = ipx.interp1d(x, xp, fp, method="cubic", period=2 * np.pi)
+    np.testing.assert_allclose(fq, np.sin(x), rtol=1e-6, atol=1e-2)
+    assert_parity(fq, O.interp1d(x, xp, fp, method="cubic", period=2 * np.pi))
+    xk = np.linspace(-4, 5, 10)
+    f = np.heaviside(xk - 1.5, 0) + 0.1 * xk
+    xq = np.linspace(-4, 5, 1000)
+    dfc = ipx.interp1d(xq, xk, f, derivative=1, method="cubic")
+    dfm = ipx.interp1d(xq, xk, f, derivative=1, method="monotonic")
+    dfm0 = ipx.interp1d(xq, xk, f, derivative=1, method="monotonic-0")
+    assert dfc.min() < 0 and dfm.min() > 0 and dfm0.min() >= 0
+    np.testing.assert_allclose(dfm0[np.array([0, -1])], 0, atol=1e-12)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex64, np.complex128])
+@pytest.mark.parametrize("scalar", [False, True])
+def test_reference_test_interp2d(dtype, scalar):
+    # tests/test_interpolate.py:155-235
+    cplx = np.iscomplexobj(np.zeros(1, dtype))
+    xp = np.real(np.linspace(0, 3 * np.pi, 99).astype(dtype))
+    yp = np.real(np.linspace(0, 2 * np.pi, 40).astype(dtype))
+    xxp, yyp = np.meshgrid(xp, yp, indexing="ij")
+    f = (lambda x, y: np.sin(x) * np.cos(y) * (1 + 1j)) if cplx else (lambda x, y: np.sin(x) * np.cos(y))
+    fp = f(xxp, yyp).astype(dtype)
+    if scalar:
+        x, y = 0.0, 0.0
+    else:
+        x = np.real(np.linspace(0, 3 * np.pi, 1000).astype(dtype))
+        y = np.real(np.linspace(0, 2 * np.pi, 1000).astype(dtype))
+    per = (2 * np.pi, 2 * np.pi)
+    tol = {"nearest": (1e-2, 1), "linear": (1e-4, 1e-2), "cubic": (1e-5, 2e-3), "cubic2": (1e-5, 2e-3),
+           "catmull-rom": (1e-5, 2e-3), "cardinal": (1e-5, 2e-3), "akima": (1e-5, 2e-3),
+           "monotonic": (1e-2, 1e-3), "monotonic-0": (1e-2, 2e-2)}
+    for form, interp in (("fn", ipx.interp2d), ("cls", lambda xq, yq, *a, **k: ipx.Interpolator2D(*a, **k)(xq, yq))):
+        ointerp = O.interp2d if form == "fn" else (lambda xq, yq, *a, **k: O.Interpolator2D(*a, **k)(xq, yq))
+        for m, (rtol, atol) in tol.items():
+            if cplx and m == "akima":
+                continue
+            fq = interp(x, y, xp, yp, fp, method=m, period=per)
+            assert fq.dtype == np.result_type(x, y, xp, yp, fp)
+            np.testing.assert_allclose(fq, f(x, y), rtol=rtol, atol=atol, err_msg=m)
+            assert_parity(fq, ointerp(x, y, xp, yp, fp, method=m, period=per), f"{form} {m}")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex64, np.complex128])
+@pytest.mark.parametrize("scalar", [False, True])
+def test_reference_test_interp3d(dtype, scalar):
+    # tests/test_interpolate.py:262-337
+    cplx = np.iscomplexobj(np.zeros(1, dtype))
+    xp = np.real(np.linspace(0, np.pi, 20).astype(dtype))
+    yp = np.real(np.linspace(0, 2 * np.pi, 30).astype(dtype))
+    zp = np.real(np.linspace(0, 3, 25).astype(dtype))
+    xxp, yyp, zzp = np.meshgrid(xp, yp, zp, indexing="ij")
+    g = lambda x, y, z: np.sin(x) * np.cos(y) * z**2
+    f = (lambda x, y, z: g(x, y, z) * (1 + 1j)) if cplx else g
+    fp = f(xxp, yyp, zzp).astype(dtype)
+    if scalar:
+        x, y, z = 0.0, 0.0, 0.0
+    else:
+        x = np.real(np.linspace(0, np.pi, 1000).astype(dtype))
+        y = np.real(np.linspace(0, 2 * np.pi, 1000).astype(dtype))
+        z = np.real(np.linspace(0, 3, 1000).astype(dtype))
+    tol = {"nearest": (1e-2, 1), "linear": (1e-3, 1e-1), "cubic": (1e-5, 5.5e-3), "cubic2": (1e-5, 5.5e-3),
+           "catmull-rom": (1e-5, 5.5e-3), "cardinal": (1e-5, 5.5e-3), "monotonic": (1e-2, 1e-2),
+           "monotonic-0": (1e-2, 0.3)}
+    for form, interp in (("fn", ipx.interp3d),
+                         ("cls", lambda a, b, c, *r, **k: ipx.Interpolator3D(*r, **k)(a, b, c))):
+        ointerp = O.interp3d if form == "fn" else (lambda a, b, c, *r, **k: O.Interpolator3D(*r, **k)(a, b, c))
+        for m, (rtol, atol) in tol.items():
+            fq = interp(x, y, z, xp, yp, zp, fp, method=m)
+            assert fq.dtype == np.result_type(x, y, z, xp, yp, zp, fp)
+            np.testing.assert_allclose(fq, f(x, y, z), rtol=rtol, atol=atol, err_msg=m)
+            assert_parity(fq, ointerp(x, y, z, xp, yp, zp, fp, method=m), f"{form} {m}")
+
+
+def test_reference_test_vector_valued_and_extrap_float():
+    # tests/test_interpolate.py:85-114, 238-256, 340-369, 640-649
+    xp = np.linspace(0, 2 * np.pi, 100)
+    x = np.linspace(0, 2 * np.pi, 300)[10:-10]
+    f = lambda x: np.array([np.sin(x), np.cos(x)])
+    fp = f(xp).T
+    for m in ("nearest", "linear", "cubic", "cubic2", "cardinal", "catmull-rom", "monotonic", "monotonic-0"):
+        rtol, atol = TOL_1D[m]
+        fq = ipx.interp1d(x, xp, fp, method=m)
+        np.testing.assert_allclose(fq, f(x).T, rtol=rtol, atol=max(atol, 1e-2 if m == "monotonic-0" else 0))
+        assert_parity(fq, O.interp1d(x, xp, fp, method=m), m)
+    xk = np.linspace(0, 10, 10)
+    yk = np.linspace(0, 8, 8)
+    z = np.zeros((10, 8)) + 1.0
+    ip = ipx.Interpolator2D(xk, yk, z, extrap=0.0)
+    np.testing.assert_allclose(ip(4.5, 5.3), 1.0)
+    np.testing.assert_allclose(ip(-4.5, 5.3), 0.0)
+    np.testing.assert_allclose(ip(4.5, -5.3), 0.0)
+    # 3-D vector valued
+    xs = np.linspace(0, np.pi, 1000); ys = np.linspace(0, 2 * np.pi, 1000); zs = np.linspace(0, 3, 1000)
+    xp = np.linspace(0, np.pi, 20); yp = np.linspace(0, 2 * np.pi, 30); zp = np.linspace(0, 3, 25)
+    xxp, yyp, zzp = np.meshgrid(xp, yp, zp, indexing="ij")
+    g = lambda x, y, z: np.array([np.sin(x) * np.cos(y) * z**2, 0.1 * (x + y - z)])
+    fp = g(xxp.T, yyp.T, zzp.T).T
+    for m, (rtol, atol) in {"nearest": (1e-2, 1), "linear": (1e-3, 1e-1), "cubic": (1e-5, 5e-3),
+                            "monotonic": (1e-2, 1e-2)}.items():
+        fq = ipx.interp3d(xs, ys, zs, xp, yp, zp, fp, method=m)
+        np.testing.assert_allclose(fq, g(xs, ys, zs).T, rtol=rtol, atol=atol)
+        assert_parity(fq, O.interp3d(xs, ys, zs, xp, yp, zp, fp, method=m), m)
+
+
+# ------------------------------------------------------------------ "grad wrt xq" = derivative+1
+def test_derivative_kernel_matches_finite_differences():
+    """The jax.ffi binding's JVP for xq re-enters the kernel with derivative+1
+    (INTEGRATION.md); check that this is the derivative of the derivative-0 kernel."""
+    rng = np.random.default_rng(9)
+    xp = np.linspace(0, 1, 12); yp = np.linspace(0, 2, 9); zp = np.linspace(-1, 1, 10)
+    f = rng.normal(size=(12, 9, 10))
+    ip = ipx.Interpolator3D(xp, yp, zp, f, "cubic")
+    q = [rng.uniform(a[1], a[-2], 200) for a in (xp, yp, zp)]
+    h = 1e-6
+    for ax in range(3):
+        qp = [v.copy() for v in q]; qm = [v.copy() for v in q]
+        qp[ax] += h; qm[ax] -= h
+        fd = (ip(*qp) - ip(*qm)) / (2 * h)
+        d = [0, 0, 0]; d[ax] = 1
+        np.testing.assert_allclose(ip(*q, *d), fd, rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------ C ABI specifics
+def test_abi_device_params_graph_capture_and_errors():
+    lib = L.load()
+    dev = torch.device("cuda")
+    rng = np.random.default_rng(10)
+    n = 64
+    x = torch.linspace(0, 1, n, dtype=torch.float64, device=dev)
+    f = torch.from_numpy(rng.normal(size=n)).to(dev)
+    fx = api._slopes_dev(x, f, "cubic", 0, {})
+    q = torch.from_numpy(rng.uniform(-0.1, 1.1, 4096)).to(dev)
+    out_h = torch.empty(4096, dtype=torch.float64, device=dev)
+    out_d = torch.empty_like(out_h)
+    out_g = torch.empty_like(out_h)
+    p = api._make_params(1, (1,), (False, 3.0), (None,))
+    tabs = api._ptr_array([f, fx])
+    stream = torch.cuda.current_stream().cuda_stream
+    rc = lib.ipx_eval1d_f64(q.data_ptr(), 4096, x.data_ptr(), None, n, tabs, L.IPX_SOA, 1, L.IPX_CUBIC, 0,
+                            C.byref(p), 0, out_h.data_ptr(), None, stream)
+    assert rc == L.IPX_OK
+    # traced operands from DEVICE memory (what an XLA custom call would hand over)
+    pbytes = torch.frombuffer(bytearray(bytes(p)), dtype=torch.uint8).to(dev)
+    rc = lib.ipx_eval1d_f64(q.data_ptr(), 4096, x.data_ptr(), None, n, tabs, L.IPX_SOA, 1, L.IPX_CUBIC, 0,
+                            C.cast(C.c_void_p(pbytes.data_ptr()), C.POINTER(L.Params)), 1,
+                            out_d.data_ptr(), None, stream)
+    assert rc == L.IPX_OK
+    torch.cuda.synchronize()
+    assert torch.equal(torch.nan_to_num(out_h, nan=-7.0), torch.nan_to_num(out_d, nan=-7.0))
+    want = O.interp1d(q.cpu().numpy(), x.cpu().numpy(), f.cpu().numpy(), "cubic", 1, (False, 3.0))
+    assert_parity(out_h.cpu().numpy(), want)
+    # the call only enqueues on the given stream: it can be captured in a CUDA graph ("jit")
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            rc = lib.ipx_eval1d_f64(q.data_ptr(), 4096, x.data_ptr(), None, n, tabs, L.IPX_SOA, 1,
+                                    L.IPX_CUBIC, 0, C.byref(p), 0, out_g.data_ptr(), None,
+                                    torch.cuda.current_stream().cuda_stream)
+            assert rc == L.IPX_OK
+    out_g.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(torch.nan_to_num(out_h, nan=-7.0), torch.nan_to_num(out_g, nan=-7.0))
+    # error codes, not aborts
+    assert lib.ipx_eval1d_f64(q.data_ptr(), 4096, x.data_ptr(), None, 1, tabs, L.IPX_SOA, 1, L.IPX_CUBIC, 0,
+                              C.byref(p), 0, out_h.data_ptr(), None, stream) == L.IPX_EINVAL
+    assert lib.ipx_eval1d_f64(q.data_ptr(), 4096, x.data_ptr(), None, n, tabs, 7, 1, L.IPX_CUBIC, 0,
+                              C.byref(p), 0, out_h.data_ptr(), None, stream) == L.IPX_EINVAL
+    assert lib.ipx_eval1d_f64(q.data_ptr(), 0, x.data_ptr(), None, n, tabs, L.IPX_SOA, 1, L.IPX_CUBIC, 0,
+                              C.byref(p), 0, None, None, stream) == L.IPX_OK  # empty input
+
+
+def test_torch_inputs_stay_on_device_and_empty_queries():
+    dev = torch.device("cuda")
+    xp = torch.linspace(0, 1, 20, dtype=torch.float64, device=dev)
+    fp = torch.sin(xp)
+    q = torch.rand(1000, dtype=torch.float64, device=dev)
+    out = ipx.interp1d(q, xp, fp)
+    assert isinstance(out, torch.Tensor) and out.is_cuda and out.shape == (1000,)
+    assert_parity(out.cpu().numpy(), O.interp1d(q.cpu().numpy(), xp.cpu().numpy(), fp.cpu().numpy()))
+    empty = ipx.interp1d(np.zeros(0), xp.cpu().numpy(), fp.cpu().numpy())
+    assert empty.shape == (0,)
+    e3 = ipx.interp3d(np.zeros(0), np.zeros(0), np.zeros(0), np.arange(3.), np.arange(3.), np.arange(3.),
+                      np.zeros((3, 3, 3, 2)))
+    assert e3.shape == (0, 2)
+
+
+# ------------------------------------------------------------------ full-size properties (C3 / C4 shapes)
+def test_full_size_properties_c4():
+    """256^3 tricubic, period on x and y, extrap on z, 2^24 queries: size-independent
+    properties that need no oracle -- exactness at the knots, constants reproduced,
+    linearity in the table, invariance under query permutation, periodic images agree,
+    plus oracle parity on a 2^14-query subsample."""
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(1234 + 4)
+    n = 256
+    P = 2 * np.pi
+    x = torch.arange(n, dtype=torch.float64, device=dev) * (P / n)
+    z = torch.linspace(0, 1, n, dtype=torch.float64, device=dev)
+    f1 = torch.randn((n, n, n), dtype=torch.float64, device=dev, generator=g)
+    f2 = torch.randn((n, n, n), dtype=torch.float64, device=dev, generator=g)
+    period = (P, P, None)
+    extrap = ((True, True), (True, True), (True, 0.0))
+    ip1 = ipx.Interpolator3D(x, x, z, f1, "cubic", extrap, period)
+    nq = 1 << 24
+    xq = (torch.rand(nq, dtype=torch.float64, device=dev, generator=g) * 3 - 1) * P
+    yq = (torch.rand(nq, dtype=torch.float64, device=dev, generator=g) * 3 - 1) * P
+    zq = torch.rand(nq, dtype=torch.float64, device=dev, generator=g) * 1.1 - 0.05
+    r1 = ip1(xq, yq, zq)
+    # fill value above the open axis, polynomial continuation below it
+    assert torch.all(r1[zq > 1.0] == 0.0) and torch.isfinite(r1).all()
+    # permutation invariance (bitwise): each query is independent of its neighbours
+    perm = torch.randperm(nq, device=dev, generator=g)
+    assert torch.equal(ip1(xq[perm], yq[perm], zq[perm]), r1[perm])
+    # periodic images: q and q + P land in the same cell up to the rounding of the wrap
+    rimg = ip1(xq + P, yq - P, zq)
+    assert torch.allclose(rimg, r1, rtol=0, atol=1e-9 * float(f1.abs().max()) * n)
+    # linearity in the table (slopes are linear for method="cubic")
+    ip2 = ipx.Interpolator3D(x, x, z, f2, "cubic", extrap, period)
+    ip12 = ipx.Interpolator3D(x, x, z, 2.0 * f1 - 3.0 * f2, "cubic", extrap, period)
+    lin = 2.0 * r1 - 3.0 * ip2(xq, yq, zq)
+    assert torch.allclose(ip12(xq, yq, zq), lin, rtol=1e-11, atol=1e-11 * float(lin.abs().max()))
+    # constants are reproduced exactly up to rounding; knots are reproduced
+    ipc = ipx.Interpolator3D(x, x, z, torch.full_like(f1, 3.25), "cubic", True, period)
+    assert torch.allclose(ipc(xq, yq, zq), torch.full_like(r1, 3.25), rtol=1e-13, atol=0)
+    ii = torch.randint(0, n, (4096,), device=dev, generator=g)
+    jj = torch.randint(0, n, (4096,), device=dev, generator=g)
+    kk = torch.randint(0, n, (4096,), device=dev, generator=g)
+    atk = ip1(x[ii], x[jj], z[kk])
+    assert torch.allclose(atk, f1[ii, jj, kk], rtol=1e-13, atol=1e-13)
+    # oracle parity on a subsample (class form: slopes on the un-padded table)
+    m = 1 << 14
+    want = O.Interpolator3D(x.cpu().numpy(), x.cpu().numpy(), z.cpu().numpy(), f1.cpu().numpy(), "cubic",
+                            extrap, period)(xq[:m].cpu().numpy(), yq[:m].cpu().numpy(), zq[:m].cpu().numpy())
+    assert_parity(r1[:m].cpu().numpy(), want)
+
+
+def test_full_size_properties_c3():
+    """2048^2 bicubic, 2^24 random queries, derivative (0,0) and (1,0), f64."""
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(1234 + 3)
+    n = 2048
+    x = torch.linspace(0, 1, n, dtype=torch.float64, device=dev)
+    f = torch.randn((n, n), dtype=torch.float64, device=dev, generator=g)
+    ip = ipx.Interpolator2D(x, x, f, "cubic", False)
+    nq = 1 << 24
+    xq = torch.rand(nq, dtype=torch.float64, device=dev, generator=g) * 1.02 - 0.01
+    yq = torch.rand(nq, dtype=torch.float64, device=dev, generator=g) * 1.02 - 0.01
+    r0 = ip(xq, yq)
+    r1 = ip(xq, yq, 1, 0)
+    outside = (xq < 0) | (xq > 1) | (yq < 0) | (yq > 1)
+    assert torch.equal(torch.isnan(r0), outside) and torch.equal(torch.isnan(r1), outside)
+    m = 1 << 14
+    o = O.Interpolator2D(x.cpu().numpy(), x.cpu().numpy(), f.cpu().numpy(), "cubic", False)
+    xs, ys = xq[:m].cpu().numpy(), yq[:m].cpu().numpy()
+    assert_parity(r0[:m].cpu().numpy(), o(xs, ys))
+    assert_parity(r1[:m].cpu().numpy(), o(xs, ys, 1, 0))
