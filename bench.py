@@ -1,0 +1,460 @@
+#!/usr/bin/env python
+"""bench.py -- the headline measurement: tricubic interp3d queries/s on B200 (BASELINE.json
+`metric`, config C4: 256^3 grid, period on x and y, extrap on z, 1e8 queries per GPU, f64).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path (Interpolator3D.__call__ -> ipx_eval3d_f64, one kernel
+launch) over one batch of `--nq` synthetic queries per GPU.  Rank 0 prints ONE JSON line.
+
+  value     whole-job queries/s with queries, tables and results resident in HBM
+  e2e       the same call fed from pinned HOST buffers, host<->device copies inside the
+            timed region (what a caller holding NumPy-side data sees)
+  roofline  algorithmic bytes per launch / CUDA-event launch time vs the measured HBM peak
+  cpu_baseline  the oracle's OpenMP C restatement of the reference algorithm (dense 64x64
+            contraction) on the host cores, on a bounded sample of the same workload
+
+Multi-GPU (torchrun, one rank per GPU): tables are broadcast once with NCCL, queries are
+sharded (each rank owns --nq of them: weak scaling), there is no per-call collective; the
+reported time is the max over ranks.
+
+The oracle (oracle/) is executed here only as the CPU baseline / reference arm, never on the
+measured GPU path.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEED = 1234 + 4
+TWO_PI = 2.0 * np.pi
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nq", type=int, default=100_000_000, help="queries per GPU per step")
+    ap.add_argument("--grid", type=int, default=256)
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--cpu-sample", type=int, default=1 << 21, help="queries per CPU baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------
+# workload C4: definitions shared by both arms
+# ------------------------------------------------------------------------------------------
+PERIOD = (TWO_PI, TWO_PI, None)
+EXTRAP = ((True, True), (True, True), (True, 0.0))
+
+
+def workload_name(args):
+    return (f"C4 interp3d tricubic {args.grid}^3 {args.dtype}, period=(2pi,2pi,None), "
+            f"extrap z=(True,0.0), {args.nq:.3g} queries/GPU")
+
+
+def algorithmic_bytes(nq, n, elem):
+    """every query coordinate read once, every result written once, every table
+    element read once, knots once."""
+    return nq * (3 * elem + elem) + 8 * n**3 * elem + 3 * n * elem
+
+
+def host_knots(n, np_dt):
+    x = (np.arange(n) * (TWO_PI / n)).astype(np_dt)
+    z = np.linspace(0.0, 1.0, n).astype(np_dt)
+    return x, x.copy(), z
+
+
+# ------------------------------------------------------------------------------------------
+# clocks: sampled DURING the timed regions (NVML if importable, nvidia-smi otherwise)
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {
+        0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+        0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+        0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
+    }
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reason_bits = 0
+        self.max_mhz = None
+        self.active = False
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
+
+    def _loop(self):
+        nv = self._nvml
+        while not self._stop.is_set():
+            if self.active:
+                try:
+                    if nv is not None:
+                        self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                        self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                    else:
+                        out = subprocess.run(
+                            ["nvidia-smi", "-i", str(self.index),
+                             "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.active",
+                             "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5,
+                        ).stdout.strip().split(",")
+                        self.samples.append(float(out[0]))
+                        self.max_mhz = float(out[1])
+                        self.reason_bits |= int(out[2].strip(), 16)
+                except Exception:
+                    pass
+            time.sleep(0.005)
+
+    def start(self):
+        self._thread = threading.Thread(target=self._loop, daemon=True)
+        self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=2)
+
+    def summary(self):
+        reasons = [name for bit, name in self.REASONS.items() if self.reason_bits & bit and name != "gpu_idle"]
+        return {
+            "sm_mhz": float(np.median(self.samples)) if self.samples else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": reasons,
+            "samples": len(self.samples),
+        }
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle's C restatement (OpenMP, all host threads)
+# ------------------------------------------------------------------------------------------
+def cpu_setup(args):
+    """Tables on the host, wrap-padded the way the reference pads them per call
+    (_make_periodic, _spline.py:1108-1135).  Slopes come from the NumPy oracle's approx_df
+    on the un-padded table (class form, _spline.py:380-393)."""
+    from oracle import interpax_np as O
+
+    np_dt = np.float64  # the C restatement computes in f64
+    n = args.grid
+    x, y, z = host_knots(n, np_dt)
+    rng = np.random.default_rng(SEED)
+    f = rng.standard_normal((n, n, n))
+    tabs = {"f": f}
+    for name, src, ax in (("fx", "f", 0), ("fy", "f", 1), ("fz", "f", 2), ("fxy", "fx", 1),
+                          ("fxz", "fx", 2), ("fyz", "fy", 2), ("fxyz", "fxy", 2)):
+        tabs[name] = O.approx_df((x, y, z)[ax], tabs[src], "cubic", ax)
+    names = O.TABLES_3D
+    arrs = [tabs[nm] for nm in names]
+    one = np.zeros(1)
+    _, xp, *arrs = O._make_periodic(one, x, TWO_PI, 0, *arrs)
+    _, yp, *arrs = O._make_periodic(one, y, TWO_PI, 1, *arrs)
+    arrs = [np.ascontiguousarray(a) for a in arrs]
+    return (xp, yp, z), arrs
+
+
+def cpu_queries(nq, seed):
+    rng = np.random.default_rng(seed)
+    xq = rng.uniform(-TWO_PI, 2 * TWO_PI, nq)
+    yq = rng.uniform(-TWO_PI, 2 * TWO_PI, nq)
+    zq = rng.uniform(-0.05, 1.05, nq)
+    return xq, yq, zq
+
+
+def cpu_step(knots, arrs, q):
+    from oracle import interpax_c as OC
+
+    # the per-call wrap of the queries (xq % period) belongs to the call
+    xq = q[0] % TWO_PI
+    yq = q[1] % TWO_PI
+    return OC.interp_cubic((xq, yq, q[2]), knots, arrs, 0, ((True, True), (True, True), (True, 0.0)))
+
+
+def cpu_measure(args, steps, warmup):
+    from oracle import interpax_c as OC
+
+    knots, arrs = cpu_setup(args)
+    q = cpu_queries(args.cpu_sample, SEED + 1)
+    for _ in range(max(1, warmup)):
+        cpu_step(knots, arrs, q)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(knots, arrs, q)
+    dt = (time.perf_counter() - t0) / steps
+    return {
+        "value": args.cpu_sample / dt,
+        "unit": "queries/s",
+        "cores": OC.num_threads(),
+        "kind": "port",
+        "sample": (f"{args.cpu_sample} random-order queries per step of the same C4 workload (f64), "
+                   f"OpenMP C restatement of the reference's dense 64x64 tricubic path; tables "
+                   f"pre-padded once (the reference re-pads per call), {steps} steps"),
+        "ms_per_step": dt * 1e3,
+    }
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host cores.  The reference itself
+    (pure Python on JAX) cannot be installed here -- no jax/jaxlib/equinox/lineax wheels and
+    no network -- so this times the oracle's C port, which always exists."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    r = cpu_measure(args, steps, max(1, min(args.warmup, 3)))
+    line = {
+        "impl": "reference",
+        "metric": "tricubic interp3d queries/s",
+        "value": r["value"],
+        "unit": "queries/s",
+        "n_gpus": args.gpus,
+        "steps": steps,
+        "warmup": args.warmup,
+        "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args), "query_order": "random",
+                   "note": "CPU arm evaluates a bounded sample per step"},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import interpax_b200 as ipx
+    from interpax_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()  # fail loudly here if libipx.so is missing
+
+    tdt = torch.float64 if args.dtype == "f64" else torch.float32
+    np_dt = np.float64 if args.dtype == "f64" else np.float32
+    elem = 8 if args.dtype == "f64" else 4
+    n, nq = args.grid, args.nq
+
+    # ---- tables: generated on rank 0, broadcast ONCE (no per-call collective) ----
+    xk, yk, zk = (torch.from_numpy(a).to(dev) for a in host_knots(n, np_dt))
+    f = torch.empty((n, n, n), dtype=tdt, device=dev)
+    if rank == 0:
+        g0 = torch.Generator(device=dev).manual_seed(SEED)
+        f.copy_(torch.randn((n, n, n), dtype=tdt, device=dev, generator=g0))
+    if world > 1:
+        dist.broadcast(f, src=0)
+    ip = ipx.Interpolator3D(xk, yk, zk, f, "cubic", EXTRAP, PERIOD)  # slopes + pack, not timed
+
+    # ---- queries: this rank's shard, random order and cell-sorted order ----
+    g = torch.Generator(device=dev).manual_seed(SEED + 1 + rank)
+    xq = (torch.rand(nq, dtype=tdt, device=dev, generator=g) * 3 - 1) * TWO_PI
+    yq = (torch.rand(nq, dtype=tdt, device=dev, generator=g) * 3 - 1) * TWO_PI
+    zq = torch.rand(nq, dtype=tdt, device=dev, generator=g) * 1.1 - 0.05
+    h = TWO_PI / n
+    ix = torch.remainder(xq, TWO_PI).div_(h).floor_().clamp_(0, n - 1).to(torch.int32)
+    iy = torch.remainder(yq, TWO_PI).div_(h).floor_().clamp_(0, n - 1).to(torch.int32)
+    iz = (zq * (n - 1)).floor_().clamp_(0, n - 2).to(torch.int32)
+    key = (ix * n + iy) * n + iz
+    del ix, iy, iz
+    order = torch.argsort(key)
+    del key
+    sq = [xq[order], yq[order], zq[order]]
+    del order
+    rq = [xq, yq, zq]
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        sampler.active = True
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        sampler.active = False
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms / steps
+
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+    launches = 0
+
+    ms_sorted = timed(lambda: ip(*sq), steps, warmup)
+    launches += steps
+    ms_random = timed(lambda: ip(*rq), steps, warmup)
+    launches += steps
+
+    # ---- spot parity of what was just timed (first 4096 sorted queries), rank 0 ----
+    parity = None
+    if rank == 0:
+        from oracle import interpax_np as O
+
+        m = 4096
+        got = ip(*[q[:m] for q in sq]).cpu().numpy()
+        want = O.Interpolator3D(xk.cpu().numpy(), yk.cpu().numpy(), zk.cpu().numpy(), f.cpu().numpy(),
+                                "cubic", EXTRAP, PERIOD)(*[q[:m].cpu().numpy() for q in sq])
+        rtol = 1e-12 if args.dtype == "f64" else 1e-5
+        err = float(np.max(np.abs(got - want)) / np.max(np.abs(want)))
+        parity = {"checked": m, "max_err_over_max_abs": err, "ok": bool(err <= rtol)}
+
+    # ---- e2e: pinned host buffers in, host result out, through the public API ----
+    e2e = None
+    if not args.no_e2e:
+        hq = [torch.empty(nq, dtype=tdt).pin_memory() for _ in range(3)]
+        for dst, src in zip(hq, sq):
+            dst.copy_(src)
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            out = ip(*hq)  # CPU tensors in -> CPU (pinned) tensor out
+            return out
+
+        e_steps = max(3, min(steps, 5))
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        sampler.active = True
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / e_steps
+        sampler.active = False
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        barrier()
+        launches += e_steps * ipx.api.launches_per_host_call(nq)
+        e2e = {"value": world * nq / dt, "unit": "queries/s", "h2d_bytes_per_step": 3 * nq * elem,
+               "d2h_bytes_per_step": nq * elem, "ms_per_step": dt * 1e3, "steps": e_steps,
+               "query_order": "cell-sorted"}
+        del hq
+
+    if rank == 0:
+        sampler.stop()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"])
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    bytes_launch = algorithmic_bytes(nq, n, elem)
+    ach_sorted = bytes_launch / (ms_sorted * 1e-3) / 1e9
+    ach_random = bytes_launch / (ms_random * 1e-3) / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("eval3d_f64_aos_sorted_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    line = {
+        "metric": "tricubic interp3d queries/s",
+        "value": world * nq / (ms_sorted * 1e-3),
+        "unit": "queries/s",
+        "n_gpus": world,
+        "steps": steps,
+        "warmup": warmup,
+        "ms_per_step": ms_sorted,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": args.dtype,
+        "data": "synthetic",
+        "config": {
+            "workload": workload_name(args),
+            "query_order": "cell-sorted",
+            "l2": "inputs per step (queries+results %.1f GB) exceed L2; no flush needed" % (4 * nq * elem / 1e9),
+            "tables": "Interpolator3D: slopes precomputed, AoS-packed, replicated per GPU (broadcast once)",
+            "parallelism": f"queries sharded x{world}, no per-call collective",
+        },
+        "roofline": {"bound": "hbm", "achieved": ach_sorted, "peak": peak, "unit": "GB/s",
+                     "frac": ach_sorted / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": bytes_launch,
+                     "kernel": "ipx::eval_kernel<double,3,CUBIC,AOS>"},
+        "random_order": {"value": world * nq / (ms_random * 1e-3), "ms_per_step": ms_random,
+                         "roofline_frac": ach_random / peak,
+                         "note": "random queries on a 1.07 GB table are bound by DRAM sector traffic "
+                                 "(>=512 B/query), not by the algorithmic bytes"},
+        "e2e": e2e,
+        "gpu_launches": launches,
+        "clocks": sampler.summary(),
+        "parity_spot_check": parity,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = {k: v for k, v in cpu_measure(args, 3, 1).items() if k != "ms_per_step"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -117,7 +117,7 @@ def _to_dev(a, np_dt: np.dtype, dev: torch.device) -> torch.Tensor:
     tdt = _NP2T[np.dtype(np_dt)]
     if isinstance(a, torch.Tensor):
         return a.to(device=dev, dtype=tdt).contiguous()
-    arr = np.ascontiguousarray(np.asarray(a, dtype=np_dt))
+    arr = np.array(a, dtype=np_dt, order="C")  # (np.ascontiguousarray would promote 0-d to 1-d)
     return torch.from_numpy(arr).to(dev)
 
 
@@ -309,12 +309,13 @@ def _make_params(ndim, derivative, extrap6, periods) -> L.Params:
 
 
 def _eval_dev(ndim, qs, knots, perms, ns, tables, layout, batch, method_class, periodic_mask,
-              params, return_index=False):
-    """One call into ipx_eval{1,2,3}d_*; everything is a device tensor already."""
+              params, return_index=False, out=None):
+    """One call into ipx_eval{1,2,3}d_* on the current stream; device tensors only."""
     lib = L.load()
     nq = qs[0].numel()
     dt = qs[0].dtype
-    out = torch.empty((nq, batch), dtype=dt, device=qs[0].device)
+    if out is None:
+        out = torch.empty((nq, batch), dtype=dt, device=qs[0].device)
     idx = torch.empty((ndim, nq), dtype=torch.int32, device=qs[0].device) if return_index else None
     fn = getattr(lib, f"ipx_eval{ndim}d_{_suffix(qs[0])}")
     args = [_ptr(q) for q in qs] + [nq] + [_ptr(k) for k in knots] + [_ptr(p) for p in perms]
@@ -325,39 +326,147 @@ def _eval_dev(ndim, qs, knots, perms, ns, tables, layout, batch, method_class, p
     return out, idx
 
 
+# --------------------------------------------------------------------------- host <-> device streaming
+# Queries that live in host memory (NumPy arrays, CPU tensors) are streamed through the GPU in
+# chunks on a few CUDA streams, so the H2D copy of chunk c+1, the kernel of chunk c and the
+# D2H copy of chunk c-1 overlap (PCIe is full duplex).  Pinned buffers make the copies truly
+# asynchronous; pageable ones still work.
+_HOST_CHUNK = 1 << 22
+_HOST_STREAMS = 3
+_pipes: dict = {}
+
+
+def launches_per_host_call(nq: int) -> int:
+    """Kernel launches one host-resident call of nq queries makes (for bench accounting)."""
+    return max(1, -(-int(nq) // _HOST_CHUNK))
+
+
+class _HostPipe:
+    def __init__(self, dev, tdt, ndim, batch):
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(_HOST_STREAMS)]
+        self.q = [[torch.empty(_HOST_CHUNK, dtype=tdt, device=dev) for _ in range(ndim)]
+                  for _ in range(_HOST_STREAMS)]
+        self.out = [torch.empty(_HOST_CHUNK * batch, dtype=tdt, device=dev) for _ in range(_HOST_STREAMS)]
+
+
+def _host_pipe(dev, tdt, ndim, batch) -> _HostPipe:
+    key = (dev.index, tdt, ndim, batch)
+    if key not in _pipes:
+        if len(_pipes) > 8:
+            _pipes.clear()
+        _pipes[key] = _HostPipe(dev, tdt, ndim, batch)
+    return _pipes[key]
+
+
+def _run_host(dev, qd, batch, launch, out_host):
+    """qd: 1-D CPU tensors; out_host: (nq, batch) CPU tensor; launch(dq, dout) enqueues the
+    kernel on the current stream."""
+    ndim = len(qd)
+    nq = qd[0].numel()
+    if nq == 0:
+        return
+    pipe = _host_pipe(dev, qd[0].dtype, ndim, batch)
+    cur = torch.cuda.current_stream()
+    for s in pipe.streams:
+        s.wait_stream(cur)
+    for c, lo in enumerate(range(0, nq, _HOST_CHUNK)):
+        hi = min(nq, lo + _HOST_CHUNK)
+        m = hi - lo
+        k = c % _HOST_STREAMS
+        with torch.cuda.stream(pipe.streams[k]):
+            dq = [pipe.q[k][ax][:m] for ax in range(ndim)]
+            for ax in range(ndim):
+                dq[ax].copy_(qd[ax][lo:hi], non_blocking=True)
+            dout = pipe.out[k][: m * batch].view(m, batch)
+            launch(dq, dout)
+            out_host[lo:hi].copy_(dout, non_blocking=True)
+    for s in pipe.streams:
+        s.synchronize()
+
+
 # --------------------------------------------------------------------------- front end
 class _Inputs:
     """dtype / shape front matter shared by the functional and class forms
     (_spline.py:503-521, 663-689, 882-910)."""
 
-    def __init__(self, ndim, qs, knots, f, extra_tables=()):
-        self.want_torch = any(isinstance(a, torch.Tensor) for a in (*qs, *knots, f))
+    def __init__(self, qs, knots, f_dtype_item, stored=None):
+        self.want_torch = any(isinstance(a, torch.Tensor) for a in (*qs, *knots)) or (
+            stored.want_torch if stored is not None else isinstance(f_dtype_item, torch.Tensor))
         self.dev = _device()
         self.xdt = _promote([*knots, *qs])
         errorif(np.issubdtype(self.xdt, np.complexfloating), TypeError, "knots and queries must be real")
-        self.fdt = np.dtype(np.result_type(_promote([f]), self.xdt))
+        fdt = stored.fdt if stored is not None else _promote([f_dtype_item])
+        self.fdt = np.dtype(np.result_type(fdt, self.xdt))
         self.complex = bool(np.issubdtype(self.fdt, np.complexfloating))
         # the kernels compute in one real type T = the real part of result_type(f, x)
         self.rdt = np.dtype(np.float64) if self.fdt in (np.float64, np.complex128) else np.dtype(np.float32)
+        self.tdt = _NP2T[self.rdt]
 
     def coords(self, a):
         t = _to_dev(a, self.xdt, self.dev)
-        return t if self.rdt == self.xdt else t.to(_NP2T[self.rdt])
+        return t if t.dtype == self.tdt else t.to(self.tdt)
 
     def table(self, a):
         t = _to_dev(a, self.fdt, self.dev)
         if self.complex:
             t = torch.view_as_real(t).contiguous()
-        return t if t.dtype == _NP2T[self.rdt] else t.to(_NP2T[self.rdt])
+        return t if t.dtype == self.tdt else t.to(self.tdt)
 
-    def finish(self, out: torch.Tensor, outshape):
+    def queries(self, qs):
+        """-> (list of flat 1-D tensors, query shape, host_mode).  Host-resident queries stay on
+        the host (they are streamed); if any query is a CUDA tensor all go to the device."""
+        ts = []
+        for q in qs:
+            if isinstance(q, torch.Tensor):
+                t = q
+            else:
+                t = torch.from_numpy(np.array(q, dtype=self.xdt, order="C"))
+            ts.append(t)
+        host = all(not t.is_cuda for t in ts)
+        if not host:
+            ts = [t.to(self.dev) for t in ts]
+        ts = [t if t.dtype == self.tdt else t.to(self.tdt) for t in ts]
+        if len(ts) > 1:
+            ts = list(torch.broadcast_tensors(*ts))
+        shape = tuple(ts[0].shape)
+        ts = [t.contiguous().reshape(-1) for t in ts]
+        return ts, shape, host
+
+    def finish(self, out: torch.Tensor, outshape, host):
         if self.complex:
-            out = torch.view_as_complex(out.reshape(tuple(outshape) + (2,)).contiguous())
+            out = torch.view_as_complex(out.reshape(tuple(outshape) + (2,)))
         out = out.reshape(tuple(outshape))
         tdt = _NP2T[self.fdt]
         if out.dtype != tdt:
             out = out.to(tdt)
-        return out if self.want_torch else out.cpu().numpy()
+        if self.want_torch:
+            return out
+        return (out if host else out.cpu()).numpy()
+
+
+def _execute(io, qs, launch, batch, tail_shape, out=None, return_index=False):
+    """Run `launch` over the queries, on the device or streamed from the host."""
+    qd, qshape, host = io.queries(qs)
+    outshape = qshape + tuple(tail_shape)
+    nq = qd[0].numel()
+    if return_index and host:
+        qd = [q.to(io.dev) for q in qd]
+        host = False
+    if out is not None:
+        errorif(not isinstance(out, torch.Tensor) or out.dtype != io.tdt or out.numel() != nq * batch
+                or not out.is_contiguous() or out.is_cuda == host, ValueError,
+                "out must be a contiguous tensor of the result dtype and size, on the side the queries are on")
+        out = out.view(nq, batch)
+    if host:
+        if out is None:
+            out = torch.empty((nq, batch), dtype=io.tdt)
+        _run_host(io.dev, qd, batch, lambda dq, dout: launch(dq, dout, False), out)
+        return io.finish(out, outshape, True)
+    res, idx = launch(qd, out, return_index)
+    final = io.finish(res, outshape, False)
+    if return_index:
+        return final, (idx if io.want_torch else idx.cpu().numpy())
+    return final
 
 
 def _shape(a):
@@ -386,6 +495,7 @@ def _interp(ndim, qs, knots, f, method, derivative, extrap, period, kwargs, retu
     names = TABLES[ndim]
     kwargs = dict(kwargs)
     given = {n: kwargs.pop(n, None) for n in names[1:]}
+    out_arg = kwargs.pop("out", None)
     if ndim == 1:
         axis = kwargs.get("axis", 0)
         errorif(axis != 0, NotImplementedError, "only axis=0 is supported")
@@ -394,15 +504,10 @@ def _interp(ndim, qs, knots, f, method, derivative, extrap, period, kwargs, retu
     fshape_user = _shape(f)
     _check_shapes(ndim, knots, fshape_user)
     errorif(method not in methods, ValueError, f"unknown method {method}")
-    io = _Inputs(ndim, qs, knots, f, given.values())
+    io = _Inputs(qs, knots, f)
     kn = [io.coords(k) for k in knots]
     errorif(io.complex and method == "akima" and any(v is None for v in given.values()),
             NotImplementedError, "akima slopes of complex data are not implemented")
-
-    qd = [io.coords(q) for q in qs]
-    qd = list(torch.broadcast_tensors(*qd)) if ndim > 1 else qd
-    outshape = tuple(qd[0].shape) + tuple(fshape_user[ndim:])
-    qd = [q.contiguous().reshape(-1) for q in qd]
 
     periods = _parse_ndarg(period, ndim)
     derivs = _parse_ndarg(derivative, ndim)
@@ -456,12 +561,12 @@ def _interp(ndim, qs, knots, f, method, derivative, extrap, period, kwargs, retu
 
     ns = [tabs["f"].shape[ax] for ax in range(ndim)]
     params = _make_params(ndim, derivs, ex, periods)
-    out, idx = _eval_dev(ndim, qd, kuse, perms, ns, tables, L.IPX_SOA, batch, mclass, mask, params,
-                         return_index)
-    res = io.finish(out, outshape)
-    if return_index:
-        return res, (idx if io.want_torch else idx.cpu().numpy())
-    return res
+
+    def launch(dq, dout, want_idx):
+        return _eval_dev(ndim, dq, kuse, perms, ns, tables, L.IPX_SOA, batch, mclass, mask, params,
+                         want_idx, dout)
+
+    return _execute(io, qs, launch, batch, fshape_user[ndim:], out_arg, return_index)
 
 
 def interp1d(xq, x, f, method="cubic", derivative=0, extrap=False, period=None, **kwargs):
@@ -490,6 +595,7 @@ def approx_df(x, f, method="cubic", axis=-1, **kwargs):
     """First derivatives at the knots.  Same contract as interpax.approx_df
     (_fd_derivs.py:9-76)."""
     want_torch = isinstance(x, torch.Tensor) or isinstance(f, torch.Tensor)
+    errorif(method not in _SLOPE_CODE, ValueError, f"got unknown method {method}")
     dev = _device()
     fdt = _promote([f])
     xdt = _promote([x])
@@ -544,7 +650,7 @@ class _InterpolatorND:
         fshape = _shape(f)
         _check_shapes(ndim, knots, fshape)
         errorif(method not in methods, ValueError, f"unknown method {method}")
-        io = _Inputs(ndim, (), knots, f)
+        io = _Inputs((), knots, f)
         kn = [io.coords(k) for k in knots]
         errorif(ndim == 1 and self.axis != 0, NotImplementedError, "only axis=0 is supported")
         errorif(io.complex and method == "akima" and any(v is None for v in given.values()),
@@ -588,33 +694,23 @@ class _InterpolatorND:
             self._pk_cache[key] = _periodic_knots_dev(self._knots[ax], per)
         return self._pk_cache[key]
 
-    def _call(self, qs, derivative, return_index=False):
+    def _call(self, qs, derivative, out=None, return_index=False):
         ndim = self._ndim
-        io = self._io
-        want_torch = any(isinstance(q, torch.Tensor) for q in qs) or io.want_torch
-        qdt = _promote([*qs, *[np.zeros((), io.xdt)]])
+        st = self._io
         # promotion of the call mirrors interpNd(xq, self.x, self.f, ...)
-        call_io = _Inputs.__new__(_Inputs)
-        call_io.want_torch = want_torch
-        call_io.dev = io.dev
-        call_io.xdt = qdt
-        call_io.fdt = np.dtype(np.result_type(io.fdt, qdt))
-        call_io.complex = io.complex
-        call_io.rdt = np.dtype(np.float64) if call_io.fdt in (np.float64, np.complex128) else np.dtype(np.float32)
-        if call_io.rdt != io.rdt:
-            # queries wider than the stored tables: fall back to the functional form, which
-            # promotes everything exactly as the reference does
-            tabs = {n: self._user(self._tabs[n]) for n in TABLES[ndim][1:]}
+        io = _Inputs(qs, [np.zeros((), st.xdt)], None, stored=st)
+        if io.rdt != st.rdt:
+            # queries wider than the stored tables: use the functional form, which promotes
+            # everything exactly as the reference does
+            kw = {n: self._user(self._tabs[n]) for n in TABLES[ndim][1:]}
+            if out is not None:
+                kw["out"] = out
             res = _interp(ndim, qs, [k for k in self._knots], self._user(self._tabs["f"]),
-                          self.method, derivative, self.extrap, self.period, tabs, return_index)
-            if want_torch:
+                          self.method, derivative, self.extrap, self.period, kw, return_index)
+            if io.want_torch:
                 return res
             to_np = lambda t: t.cpu().numpy() if isinstance(t, torch.Tensor) else t
             return tuple(to_np(r) for r in res) if return_index else to_np(res)
-        qd = [call_io.coords(q) for q in qs]
-        qd = list(torch.broadcast_tensors(*qd)) if ndim > 1 else qd
-        outshape = tuple(qd[0].shape) + tuple(self._fshape[ndim:])
-        qd = [q.contiguous().reshape(-1) for q in qd]
         periods = _parse_ndarg(self.period, ndim)
         derivs = _parse_ndarg(derivative, ndim)
         ex = _parse_extrap(self.extrap, ndim)
@@ -632,17 +728,19 @@ class _InterpolatorND:
             tables, layout = [self._tabs["f"]], L.IPX_SOA
         ns = [self._tabs["f"].shape[ax] for ax in range(ndim)]
         params = _make_params(ndim, derivs, ex, periods)
-        out, idx = _eval_dev(ndim, qd, kuse, perms, ns, tables, layout, self._batch, mclass, mask,
-                             params, return_index)
-        res = call_io.finish(out, outshape)
-        if return_index:
-            return res, (idx if want_torch else idx.cpu().numpy())
-        return res
+        batch = self._batch
+
+        def launch(dq, dout, want_idx):
+            return _eval_dev(ndim, dq, kuse, perms, ns, tables, layout, batch, mclass, mask, params,
+                             want_idx, dout)
+
+        return _execute(io, qs, launch, batch, self._fshape[ndim:], out, return_index)
 
 
 class Interpolator1D(_InterpolatorND):
     """Convenience class for a 1D interpolated function; same contract as
-    interpax.Interpolator1D (_spline.py:48-150)."""
+    interpax.Interpolator1D (_spline.py:48-150).  ``out=`` (optional, an extension) is a
+    preallocated result tensor, e.g. pinned host memory for host-resident queries."""
 
     _ndim = 1
 
@@ -653,8 +751,8 @@ class Interpolator1D(_InterpolatorND):
     def x(self):
         return self._knots[0]
 
-    def __call__(self, xq, dx=0):
-        return self._call((xq,), (dx,))
+    def __call__(self, xq, dx=0, out=None):
+        return self._call((xq,), (dx,), out)
 
 
 class Interpolator2D(_InterpolatorND):
@@ -673,8 +771,8 @@ class Interpolator2D(_InterpolatorND):
     def y(self):
         return self._knots[1]
 
-    def __call__(self, xq, yq, dx=0, dy=0):
-        return self._call((xq, yq), (dx, dy))
+    def __call__(self, xq, yq, dx=0, dy=0, out=None):
+        return self._call((xq, yq), (dx, dy), out)
 
 
 class Interpolator3D(_InterpolatorND):
@@ -697,5 +795,5 @@ class Interpolator3D(_InterpolatorND):
     def z(self):
         return self._knots[2]
 
-    def __call__(self, xq, yq, zq, dx=0, dy=0, dz=0):
-        return self._call((xq, yq, zq), (dx, dy, dz))
+    def __call__(self, xq, yq, zq, dx=0, dy=0, dz=0, out=None):
+        return self._call((xq, yq, zq), (dx, dy, dz), out)

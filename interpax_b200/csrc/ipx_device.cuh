@@ -89,8 +89,9 @@ __device__ __forceinline__ int bin_index(const T* __restrict__ x, int n, T q, T 
     hi = x[i];
     return i;
   }
-  i = t_floor_to_int((q - x_first) * inv_h) + 1;  // saturating; NaN -> 0
-  i = min(max(i, 1), n - 1);
+  // saturating conversion (+-inf -> INT_MAX / INT_MIN); clamp BEFORE the +1 so the
+  // arithmetic cannot overflow
+  i = min(max(t_floor_to_int((q - x_first) * inv_h), 0), n - 2) + 1;
   lo = x[i - 1];
   hi = x[i];
   if (q < lo) {
