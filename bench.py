@@ -357,14 +357,15 @@ def run_ours(args):
     # ---- e2e: pinned host buffers in, host result out, through the public API ----
     e2e = None
     if not args.no_e2e:
-        hq = [torch.empty(nq, dtype=tdt).pin_memory() for _ in range(3)]
+        hq = [torch.empty(nq, dtype=tdt, pin_memory=True) for _ in range(3)]
+        hout = torch.empty(nq, dtype=tdt, pin_memory=True)
         for dst, src in zip(hq, sq):
             dst.copy_(src)
         torch.cuda.synchronize()
 
         def e2e_step():
-            out = ip(*hq)  # CPU tensors in -> CPU (pinned) tensor out
-            return out
+            # pinned CPU tensors in -> pinned CPU tensor out, through the public call
+            return ip(*hq, out=hout)
 
         e_steps = max(3, min(steps, 5))
         for _ in range(2):
@@ -386,7 +387,7 @@ def run_ours(args):
         e2e = {"value": world * nq / dt, "unit": "queries/s", "h2d_bytes_per_step": 3 * nq * elem,
                "d2h_bytes_per_step": nq * elem, "ms_per_step": dt * 1e3, "steps": e_steps,
                "query_order": "cell-sorted"}
-        del hq
+        del hq, hout
 
     if rank == 0:
         sampler.stop()

@@ -269,6 +269,12 @@ __global__ void __launch_bounds__(kThreads) eval_kernel(const EvalArgs<T, ND> a)
   }
 }
 
+}  // namespace ipx
+
+#include "ipx_eval_tile.cuh"
+
+namespace ipx {
+
 template <typename T> __global__ void bin_index_kernel(const T* __restrict__ knots, int n,
                                                        const T* __restrict__ q, int64_t nq,
                                                        int32_t* __restrict__ idx) {
@@ -360,8 +366,11 @@ static int launch_eval(const T* const* q, int64_t nq, const T* const* knots,
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int grid = grid_for(nq * batch, kThreads);
   if (method == IPX_CUBIC) {
-    if (layout == IPX_AOS) eval_kernel<T, ND, IPX_CUBIC, IPX_AOS><<<grid, kThreads, 0, s>>>(a);
-    else eval_kernel<T, ND, IPX_CUBIC, IPX_SOA><<<grid, kThreads, 0, s>>>(a);
+    if (layout == IPX_AOS) {
+      // scalar-valued packed tables: the warp-cooperative shared-memory kernel
+      const bool tiled = batch == 1 && launch_tile<T, ND>(a, s);
+      if (!tiled) eval_kernel<T, ND, IPX_CUBIC, IPX_AOS><<<grid, kThreads, 0, s>>>(a);
+    } else eval_kernel<T, ND, IPX_CUBIC, IPX_SOA><<<grid, kThreads, 0, s>>>(a);
   } else if (method == IPX_LINEAR) {
     eval_kernel<T, ND, IPX_LINEAR, IPX_SOA><<<grid, kThreads, 0, s>>>(a);
   } else {
