@@ -691,7 +691,14 @@ class _InterpolatorND:
     def _periodic(self, ax, per):
         key = (ax, abs(float(per)))
         if key not in self._pk_cache:
-            self._pk_cache[key] = _periodic_knots_dev(self._knots[ax], per)
+            xpad, perm = _periodic_knots_dev(self._knots[ax], per)
+            # knots already sorted inside one period (the usual case): the permutation is the
+            # identity and the kernels skip the lookup when handed NULL.  One host sync, at
+            # the first call only.
+            ident = torch.arange(perm.numel(), dtype=perm.dtype, device=perm.device)
+            if bool(torch.equal(perm, ident)):
+                perm = None
+            self._pk_cache[key] = (xpad, perm)
         return self._pk_cache[key]
 
     def _call(self, qs, derivative, out=None, return_index=False):

@@ -52,40 +52,11 @@ template <typename T> __device__ __forceinline__ T py_mod_fast(T q, T P) {
   return py_mod(q, P);
 }
 
-template <typename T> struct AxisSm {
-  const T* knots;  // shared or global
-  const T* rdx;    // shared reciprocal widths (rdx[i] = 1/(x[i]-x[i-1]) guarded) or nullptr
-};
-
+// cubic Hermite weights from the local coordinate pieces (same formulas as hermite_weights)
 template <typename T>
-__device__ __forceinline__ void locate_s(const AxisDesc<T>& A, const AxisSm<T>& S,
-                                         const AxisConst<T>& C, const ipx_axis_params& P, T qraw,
-                                         AxisLoc<T>& L, T& dxi) {
-  T q = qraw;
-  if (A.wrap) q = py_mod_fast(q, T(fabs(P.period)));
-  L.q = q;
-  L.i = bin_index(S.knots, A.nk, q, C.x_first, C.inv_h, L.x0, L.x1);
-  L.below = q < C.x_first;
-  L.above = q > C.x_last;
-  dxi = S.rdx ? S.rdx[L.i] : safe_recip(L.x1 - L.x0);
-  if (A.periodic) {
-    int s0 = L.i - 2;
-    if (s0 < 0) s0 += A.n;
-    int s1 = L.i - 1;
-    if (s1 >= A.n) s1 -= A.n;
-    L.t0 = A.perm ? A.perm[s0] : s0;
-    L.t1 = A.perm ? A.perm[s1] : s1;
-  } else {
-    L.t0 = L.i - 1;
-    L.t1 = L.i;
-  }
-}
-
-// hermite_weights with the reciprocal width supplied
-template <typename T>
-__device__ __forceinline__ void hermite_weights_r(const AxisLoc<T>& L, int order, T dxi, T w[4]) {
-  T dx = L.x1 - L.x0;
-  T t = (L.q - L.x0) * dxi;
+__device__ __forceinline__ void hermite_weights_r(T q, T x0, T x1, int order, T dxi, T w[4]) {
+  T dx = x1 - x0;
+  T t = (q - x0) * dxi;
   T tt0, tt1, tt2, tt3;
   if (order <= 0) {
     tt0 = T(1); tt1 = t; tt2 = t * t; tt3 = tt2 * t;
@@ -127,7 +98,7 @@ __device__ __forceinline__ T contract_cubic(const T (*w)[4], Loader load) {
     for (int ii = 0; ii < 2; ++ii) {
       T r[2];
       load(ii, r);
-      res += r[0] * w[0][ii] + r[1] * w[0][2 + ii];
+      res = fma(r[1], w[0][2 + ii], fma(r[0], w[0][ii], res));
     }
   } else if (ND == 2) {
 #pragma unroll
@@ -137,10 +108,10 @@ __device__ __forceinline__ T contract_cubic(const T (*w)[4], Loader load) {
       for (int jj = 0; jj < 2; ++jj) {
         T r[4];
         load(ii | (jj << 1), r);
-        p[0] += r[0] * w[1][jj] + r[1] * w[1][2 + jj];
-        p[1] += r[2] * w[1][jj] + r[3] * w[1][2 + jj];
+        p[0] = fma(r[1], w[1][2 + jj], fma(r[0], w[1][jj], p[0]));
+        p[1] = fma(r[3], w[1][2 + jj], fma(r[2], w[1][jj], p[1]));
       }
-      res += p[0] * w[0][ii] + p[1] * w[0][2 + ii];
+      res = fma(p[1], w[0][2 + ii], fma(p[0], w[0][ii], res));
     }
   } else {
 #pragma unroll
@@ -154,12 +125,13 @@ __device__ __forceinline__ T contract_cubic(const T (*w)[4], Loader load) {
           T r[8];
           load(ii | (jj << 1) | (kk << 2), r);
 #pragma unroll
-          for (int m = 0; m < 4; ++m) p[m] += r[2 * m] * w[2][kk] + r[2 * m + 1] * w[2][2 + kk];
+          for (int m = 0; m < 4; ++m)
+            p[m] = fma(r[2 * m + 1], w[2][2 + kk], fma(r[2 * m], w[2][kk], p[m]));
         }
-        v[0] += p[0] * w[1][jj] + p[1] * w[1][2 + jj];
-        v[1] += p[2] * w[1][jj] + p[3] * w[1][2 + jj];
+        v[0] = fma(p[1], w[1][2 + jj], fma(p[0], w[1][jj], v[0]));
+        v[1] = fma(p[3], w[1][2 + jj], fma(p[2], w[1][jj], v[1]));
       }
-      res += v[0] * w[0][ii] + v[1] * w[0][2 + ii];
+      res = fma(v[1], w[0][2 + ii], fma(v[0], w[0][ii], res));
     }
   }
   return res;
@@ -170,92 +142,168 @@ template <typename T> __device__ __forceinline__ int run_table_index(const AxisD
   return padded_to_table(A, p);
 }
 
-template <typename T, int ND, bool SK>
-__global__ void __launch_bounds__(kTileThreads)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+}
+
+// per-axis constants of the tile kernel, in shared memory
+template <typename T> struct TileAxis {
+  T x_first, x_last, inv_h, period;
+  int nk, n, koff;      // knots at smT[koff .. koff+nk), reciprocal widths at smT[koff+nk ..)
+  int wrap, periodic;   // flags
+  int chk_lo, chk_hi;   // extrapolation fills to apply (non-periodic axes without extrap=True)
+  int order;            // derivative order
+  T fill_lo, fill_hi;
+};
+
+template <typename T, int ND>
+__global__ void __launch_bounds__(kTileThreads, 3)
 eval_tile_kernel(const EvalArgs<T, ND> a) {
   using Cfg = TileCfg<T, ND>;
+  constexpr int LPC = 32 / Cfg::NC;          // lanes that copy one column
+  constexpr int NPR = LPC / Cfg::CH;         // nodes of a column copied per round
+  static_assert(LPC % Cfg::CH == 0 && NPR >= 1, "column copy layout");
   extern __shared__ __align__(16) char smem[];
-  __shared__ AxisConst<T> consts[ND];
-  __shared__ ipx_params params_s;
+  __shared__ TileAxis<T> AX[ND];
+  T* const smT = reinterpret_cast<T*>(smem);
 
-  // ---- per-CTA staging: constants, traced operands, knots and reciprocal widths ----
-  if (threadIdx.x < ND) axis_consts(a.ax[threadIdx.x], consts[threadIdx.x]);
-  if (threadIdx.x == 32) params_s = a.dp ? *a.dp : a.hp;
-  AxisSm<T> S[ND];
-  char* tiles = smem;
-  if (SK) {
-    T* base = reinterpret_cast<T*>(smem);
+  // ---- per-CTA staging: axis constants, traced operands, knots and reciprocal widths ----
+  if (threadIdx.x < ND) {
+    const int ax = threadIdx.x;
+    const ipx_params* pp = a.dp ? a.dp : &a.hp;
+    const ipx_axis_params p = pp->axis[ax];
+    AxisConst<T> c;
+    axis_consts(a.ax[ax], c);
+    TileAxis<T>& A = AX[ax];
+    A.x_first = c.x_first; A.x_last = c.x_last; A.inv_h = c.inv_h;
+    A.period = T(fabs(p.period));
+    A.nk = a.ax[ax].nk; A.n = a.ax[ax].n;
     int off = 0;
-#pragma unroll
-    for (int ax = 0; ax < ND; ++ax) {
-      const int nk = a.ax[ax].nk;
-      T* ks = base + off;
-      T* rs = base + off + nk;
-      for (int i = threadIdx.x; i < nk; i += kTileThreads) {
-        T xi = a.ax[ax].knots[i];
-        ks[i] = xi;
-        rs[i] = i > 0 ? safe_recip(xi - a.ax[ax].knots[i - 1]) : T(0);
-      }
-      S[ax].knots = ks;
-      S[ax].rdx = rs;
-      off += 2 * nk;
-    }
-    tiles = smem + ((off * (int)sizeof(T) + 15) & ~15);
-  } else {
-#pragma unroll
-    for (int ax = 0; ax < ND; ++ax) { S[ax].knots = a.ax[ax].knots; S[ax].rdx = nullptr; }
+    for (int k = 0; k < ax; ++k) off += 2 * a.ax[k].nk;
+    A.koff = off;
+    A.wrap = a.ax[ax].wrap; A.periodic = a.ax[ax].periodic;
+    A.chk_lo = !a.ax[ax].wrap && !p.keep_lo;
+    A.chk_hi = !a.ax[ax].wrap && !p.keep_hi;
+    A.order = p.derivative;
+    A.fill_lo = T(p.fill_lo); A.fill_hi = T(p.fill_hi);
   }
+  int knot_elems = 0;
+#pragma unroll
+  for (int ax = 0; ax < ND; ++ax) {
+    const int nk = a.ax[ax].nk;
+    for (int i = threadIdx.x; i < nk; i += kTileThreads) {
+      T xi = a.ax[ax].knots[i];
+      smT[knot_elems + i] = xi;
+      smT[knot_elems + nk + i] = i > 0 ? safe_recip(xi - a.ax[ax].knots[i - 1]) : T(0);
+    }
+    knot_elems += 2 * nk;
+  }
+  char* const tiles = smem + ((knot_elems * (int)sizeof(T) + 15) & ~15);
   __syncthreads();
-  const ipx_params& P = params_s;
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  char* tile = tiles + warp * Cfg::WARP_TILE_BYTES;
-  const T* __restrict__ tab = a.tab[0];
+  char* const tile = tiles + warp * Cfg::WARP_TILE_BYTES;
+  const char* __restrict__ tabc = reinterpret_cast<const char*>(a.tab[0]);
   const AxisDesc<T>& RA = a.ax[ND - 1];  // run axis
+  // the run of nodes is contiguous in the table unless the run axis is periodic with a
+  // permutation (un-sorted knots) or the run crosses the periodic seam
+  const bool run_identity = !RA.periodic || RA.perm == nullptr;
+  const bool want_idx = a.idx_out != nullptr;
+
+  // this lane's role in the cooperative copy: column `ccol`, chunk `lane % LPC` of each round
+  const int ccol = lane / LPC;
+  const int cl = lane - ccol * LPC;
+  const int cnode0 = cl / Cfg::CH;
+  const int cpart = cl - cnode0 * Cfg::CH;
+  const unsigned cdst0 = (unsigned)__cvta_generic_to_shared(tile) +
+                         (ccol * kRunCap + cnode0) * Cfg::STRIDE + 16 * cpart;
 
   const int64_t step = (int64_t)gridDim.x * kTileThreads;
-  int64_t qi = (int64_t)blockIdx.x * kTileThreads + threadIdx.x;
+  const int64_t q0 = (int64_t)blockIdx.x * kTileThreads + (threadIdx.x & ~31);  // warp's first query
+  if (q0 >= a.nq) return;  // whole warp idle (after the CTA barrier above)
+  const int rounds = (int)((a.nq - q0 + step - 1) / step);
 
   // software prefetch of the query stream: the loads for the next round are in flight while
   // this round gathers and contracts
+  int64_t qi = q0 + lane;
   T qn[ND];
 #pragma unroll
   for (int ax = 0; ax < ND; ++ax) qn[ax] = qi < a.nq ? a.ax[ax].q[qi] : T(0);
 
-  for (; __any_sync(0xffffffffu, qi < a.nq); qi += step) {
+  for (int round = 0; round < rounds; ++round, qi += step) {
     const bool active = qi < a.nq;
     T qc[ND];
 #pragma unroll
     for (int ax = 0; ax < ND; ++ax) qc[ax] = qn[ax];
     {
       const int64_t qnext = qi + step;
+      const bool more = qnext < a.nq;
 #pragma unroll
-      for (int ax = 0; ax < ND; ++ax) qn[ax] = qnext < a.nq ? a.ax[ax].q[qnext] : T(0);
+      for (int ax = 0; ax < ND; ++ax) qn[ax] = more ? a.ax[ax].q[qnext] : T(0);
     }
 
-    AxisLoc<T> L[ND];
-    T w[ND][4];
+    // ---- locate: wrap, interval lookup in shared memory, corner indices ----
+    int li[ND], t0[ND], t1[ND];
+    T x0[ND], x1[ND], dxi[ND];
 #pragma unroll
     for (int ax = 0; ax < ND; ++ax) {
-      T dxi;
-      locate_s(a.ax[ax], S[ax], consts[ax], P.axis[ax], qc[ax], L[ax], dxi);
-      hermite_weights_r(L[ax], P.axis[ax].derivative, dxi, w[ax]);
+      const TileAxis<T>& A = AX[ax];
+      T q = qc[ax];
+      if (A.wrap) {
+        const T P = A.period;
+        T r = q;
+        r = q < T(0) ? q + P : r;       // [-P,0): fmod leaves q, the sign fix adds P
+        r = q >= P ? q - P : r;         // [P,2P]: exact (Sterbenz)
+        if (!(q >= -P && q <= P + P)) r = py_mod(q, P);  // anything else: the exact remainder
+        q = r;
+        qc[ax] = q;
+      }
+      const int nk = A.nk;
+      const T* ks = smT + A.koff;
+      int i = min(max(t_floor_to_int((q - A.x_first) * A.inv_h), 0), nk - 2) + 1;
+      T lo = ks[i - 1], hi = ks[i];
+      // exact check of the guess against the knots (NaN fails it); the rare miss re-searches
+      if (!((q >= lo || i == 1) && (q < hi || i == nk - 1))) {
+        i = bin_index(ks, nk, q, A.x_first, A.inv_h, lo, hi);
+      }
+      li[ax] = i; x0[ax] = lo; x1[ax] = hi;
+      dxi[ax] = ks[nk + i];
+      if (A.periodic) {
+        int s0 = i - 2; s0 += s0 < 0 ? A.n : 0;
+        int s1 = i - 1; s1 -= s1 >= A.n ? A.n : 0;
+        const int32_t* pm = a.ax[ax].perm;
+        t0[ax] = pm ? pm[s0] : s0;
+        t1[ax] = pm ? pm[s1] : s1;
+      } else {
+        t0[ax] = i - 1; t1[ax] = i;
+      }
     }
 
     // ---- group lanes by cell column (all axes but the last) ----
-    unsigned long long key = 0;
+    unsigned key = 0;
+    bool key_ok = true;  // 32-bit keys suffice unless the knot vectors are huge
 #pragma unroll
-    for (int ax = 0; ax < ND - 1; ++ax) key = key * (unsigned long long)(a.ax[ax].nk + 1) + (unsigned)L[ax].i;
-    if (!active) key = ~0ull;
+    for (int ax = 0; ax < ND - 1; ++ax) {
+      const unsigned m = (unsigned)AX[ax].nk + 1u;
+      key_ok = key_ok && ((unsigned long long)key * m < 0xffff0000ull);
+      key = key * m + (unsigned)li[ax];
+    }
+    if (!active) key = 0xffffffffu;
     const unsigned same = __match_any_sync(0xffffffffu, key);
-    const bool is_leader = (__ffs(same) - 1) == lane;
-    const unsigned leaders = __ballot_sync(0xffffffffu, is_leader && active);
-    const int pz = L[ND - 1].i - 1;  // lower knot position on the run axis
+    const unsigned leaders = __ballot_sync(0xffffffffu, ((__ffs(same) - 1) == lane) && active);
+    const int pz = li[ND - 1] - 1;  // lower knot position on the run axis
+    const bool coherent = key_ok && __popc(leaders) <= kMaxGroups;
 
+    T w[ND][4];
     T res = T(0);
-    if (__popc(leaders) <= kMaxGroups) {
+    if (coherent) {
       unsigned todo = __ballot_sync(0xffffffffu, active);
+      bool have_w = false;
       while (todo) {
         const int ld = __ffs(todo) - 1;
         const unsigned grp = __shfl_sync(0xffffffffu, same, ld) & todo;
@@ -266,39 +314,52 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
         const int zmax = __reduce_max_sync(0xffffffffu, sub ? pz : -0x7fffffff);
         const int extent = zmax - zmin + 2;  // nodes per column, <= kRunCap
 
-        // column base node indices from the leader's corners
-        int64_t colbase[Cfg::NC];
+        // node index of (this lane's copy column, run position 0), from the leader's corners
+        int colnode = 0;
 #pragma unroll
-        for (int c = 0; c < Cfg::NC; ++c) {
-          int64_t idx = 0;
-#pragma unroll
-          for (int ax = 0; ax < ND - 1; ++ax) {
-            const int t0 = __shfl_sync(0xffffffffu, L[ax].t0, ld);
-            const int t1 = __shfl_sync(0xffffffffu, L[ax].t1, ld);
-            idx = idx * a.ax[ax].n + (((c >> ax) & 1) ? t1 : t0);
-          }
-          colbase[c] = idx * RA.n;
+        for (int ax = 0; ax < ND - 1; ++ax) {
+          const int c0 = __shfl_sync(0xffffffffu, t0[ax], ld);
+          const int c1 = __shfl_sync(0xffffffffu, t1[ax], ld);
+          colnode = colnode * AX[ax].n + (((ccol >> ax) & 1) ? c1 : c0);
         }
-        // ---- cooperative copy global -> shared: NC columns x extent nodes x CH chunks ----
-        const int per_col = extent * Cfg::CH;
-#pragma unroll
-        for (int c = 0; c < Cfg::NC; ++c) {
-          for (int r = lane; r < per_col; r += 32) {
-            const int node = r / Cfg::CH;
-            const int part = r - node * Cfg::CH;
+        // table position of the first node of the run, if the run is contiguous in the table
+        int zt0 = zmin;
+        bool contiguous = run_identity;
+        if (RA.periodic) {
+          zt0 = zmin - 1;
+          contiguous = contiguous && zmin >= 1 && (zmin + extent - 1) <= RA.n;
+        }
+        // ---- cooperative copy global -> shared, asynchronous (cp.async, no register staging)
+        if (contiguous) {
+          const char* src = tabc + ((size_t)colnode * RA.n + zt0) * Cfg::REC_BYTES + 16 * cl;
+          unsigned dst = cdst0;
+          for (int node = cnode0; node < extent; node += NPR) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+            src += NPR * Cfg::REC_BYTES;
+            dst += NPR * Cfg::STRIDE;
+          }
+        } else {
+          for (int node = cnode0; node < extent; node += NPR) {
             const int zt = run_table_index(RA, zmin + node);
-            const float4 v = __ldg(reinterpret_cast<const float4*>(
-                reinterpret_cast<const char*>(tab + (colbase[c] + zt) * Cfg::NT) + 16 * part));
-            *reinterpret_cast<float4*>(tile + (c * kRunCap + node) * Cfg::STRIDE + 16 * part) = v;
+            cp_async16(tile + (ccol * kRunCap + node) * Cfg::STRIDE + 16 * cpart,
+                       tabc + ((size_t)colnode * RA.n + zt) * Cfg::REC_BYTES + 16 * cpart);
           }
         }
+        // the Hermite weights do not depend on the table: compute them under the copy
+        if (!have_w) {
+#pragma unroll
+          for (int ax = 0; ax < ND; ++ax)
+            hermite_weights_r(qc[ax], x0[ax], x1[ax], AX[ax].order, dxi[ax], w[ax]);
+          have_w = true;
+        }
+        cp_async_wait_all();
         __syncwarp();
         if (sub) {
-          const int nz0 = pz - zmin;
+          const char* rec0 = tile + (pz - zmin) * Cfg::STRIDE;
           res = contract_cubic<T, ND>(w, [&](int bits, T* r) {
             const int c = bits & (Cfg::NC - 1);
-            const int node = nz0 + (bits >> (ND - 1));
-            lds_record<T, Cfg::NT>(tile + (c * kRunCap + node) * Cfg::STRIDE, r);
+            const int kk = bits >> (ND - 1);
+            lds_record<T, Cfg::NT>(rec0 + (c * kRunCap + kk) * Cfg::STRIDE, r);
           });
         }
         __syncwarp();
@@ -306,47 +367,43 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
       }
     } else if (active) {
       // ---- direct per-lane gather (incoherent queries) ----
+#pragma unroll
+      for (int ax = 0; ax < ND; ++ax)
+        hermite_weights_r(qc[ax], x0[ax], x1[ax], AX[ax].order, dxi[ax], w[ax]);
       res = contract_cubic<T, ND>(w, [&](int bits, T* r) {
-        load_record<T, ND, IPX_AOS>(a, node_index<T, ND>(a, L, bits), r);
+        size_t node = (bits & 1) ? t1[0] : t0[0];
+#pragma unroll
+        for (int ax = 1; ax < ND; ++ax) node = node * AX[ax].n + (((bits >> ax) & 1) ? t1[ax] : t0[ax]);
+        const T* p = reinterpret_cast<const T*>(tabc) + node * Cfg::NT;
+        if (ND == 1) ldg_rec2(p, r);
+        if (ND == 2) ldg_rec4(p, r);
+        if (ND == 3) ldg_rec8(p, r);
       });
     }
 
     if (active) {
-      a.out[qi] = apply_extrap<T, ND>(a, P, L, res);
-      if (a.idx_out != nullptr) {
+      // extrapolation fills, x then y then z, later axes win (_spline.py:1101-1103)
 #pragma unroll
-        for (int ax = 0; ax < ND; ++ax) a.idx_out[(int64_t)ax * a.nq + qi] = L[ax].i;
+      for (int ax = 0; ax < ND; ++ax) {
+        const TileAxis<T>& A = AX[ax];
+        if (A.chk_lo && qc[ax] < A.x_first) res = A.fill_lo;
+        if (A.chk_hi && qc[ax] > A.x_last) res = A.fill_hi;
+      }
+      a.out[qi] = res;
+      if (want_idx) {
+#pragma unroll
+        for (int ax = 0; ax < ND; ++ax) a.idx_out[(int64_t)ax * a.nq + qi] = li[ax];
       }
     }
   }
 }
 
 // dynamic shared memory the tile kernel needs
-template <typename T, int ND> static size_t tile_smem_bytes(const EvalArgs<T, ND>& a, bool sk) {
+template <typename T, int ND> static size_t tile_smem_bytes(const EvalArgs<T, ND>& a) {
   size_t knots = 0;
-  if (sk) {
-    for (int ax = 0; ax < ND; ++ax) knots += 2 * (size_t)a.ax[ax].nk * sizeof(T);
-    knots = (knots + 15) & ~(size_t)15;
-  }
+  for (int ax = 0; ax < ND; ++ax) knots += 2 * (size_t)a.ax[ax].nk * sizeof(T);
+  knots = (knots + 15) & ~(size_t)15;
   return knots + (size_t)kTileWarps * TileCfg<T, ND>::WARP_TILE_BYTES;
-}
-
-template <typename T, int ND, bool SK>
-static cudaError_t launch_tile_sk(const EvalArgs<T, ND>& a, cudaStream_t s) {
-  const size_t smem = tile_smem_bytes<T, ND>(a, SK);
-  auto kern = eval_tile_kernel<T, ND, SK>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  int dev = 0, sms = 148, per_sm = 1;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, smem);
-  if (per_sm < 1) per_sm = 1;
-  int64_t need = (a.nq + kTileThreads - 1) / kTileThreads;
-  int64_t grid = (int64_t)sms * per_sm;  // persistent: one resident wave
-  if (need < grid) grid = need;
-  kern<<<(int)grid, kTileThreads, smem, s>>>(a);
-  return cudaSuccess;
 }
 
 // true if (T, ND) has a tile kernel: records of at least 16 bytes
@@ -354,6 +411,8 @@ template <typename T, int ND> constexpr bool tile_supported() {
   return (1 << ND) * (int)sizeof(T) >= 16;
 }
 
+// Launches the tile kernel if it applies (record >= 16 B, knot vectors fit in shared memory);
+// returns false if the caller should use the generic kernel instead.
 template <typename T, int ND>
 static bool launch_tile(const EvalArgs<T, ND>& a, cudaStream_t s) {
   if constexpr (!tile_supported<T, ND>()) {
@@ -361,9 +420,21 @@ static bool launch_tile(const EvalArgs<T, ND>& a, cudaStream_t s) {
   } else {
     int total_knots = 0;
     for (int ax = 0; ax < ND; ++ax) total_knots += a.ax[ax].nk;
-    cudaError_t e = total_knots <= kSmemKnotCap ? launch_tile_sk<T, ND, true>(a, s)
-                                                : launch_tile_sk<T, ND, false>(a, s);
-    return e == cudaSuccess;
+    if (total_knots > kSmemKnotCap) return false;
+    const size_t smem = tile_smem_bytes<T, ND>(a);
+    auto kern = eval_tile_kernel<T, ND>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return false;
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, smem);
+    if (per_sm < 1) per_sm = 1;
+    int64_t need = (a.nq + kTileThreads - 1) / kTileThreads;
+    int64_t grid = (int64_t)sms * per_sm;  // persistent: one resident wave
+    if (need < grid) grid = need;
+    kern<<<(int)grid, kTileThreads, smem, s>>>(a);
+    return true;
   }
 }
 
