@@ -150,17 +150,13 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.wait_all;\n" ::: "memory");
 }
 
-// per-axis constants of the tile kernel, in shared memory
+// knot-derived constants of one axis (need device data, so they live in shared memory);
+// everything else comes straight from the kernel parameters (constant bank: no LSU traffic)
 template <typename T> struct TileAxis {
-  T x_first, x_last, inv_h, period;
-  int nk, n, koff;      // knots at smT[koff .. koff+nk), reciprocal widths at smT[koff+nk ..)
-  int wrap, periodic;   // flags
-  int chk_lo, chk_hi;   // extrapolation fills to apply (non-periodic axes without extrap=True)
-  int order;            // derivative order
-  T fill_lo, fill_hi;
+  T x_first, inv_h, x_last, pad;
 };
 
-template <typename T, int ND>
+template <typename T, int ND, bool DEVP>
 __global__ void __launch_bounds__(kTileThreads, 3)
 eval_tile_kernel(const EvalArgs<T, ND> a) {
   using Cfg = TileCfg<T, ND>;
@@ -172,25 +168,15 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
   T* const smT = reinterpret_cast<T*>(smem);
 
   // ---- per-CTA staging: axis constants, traced operands, knots and reciprocal widths ----
+  __shared__ ipx_params params_s;  // only used when the traced operands live in device memory
   if (threadIdx.x < ND) {
     const int ax = threadIdx.x;
-    const ipx_params* pp = a.dp ? a.dp : &a.hp;
-    const ipx_axis_params p = pp->axis[ax];
     AxisConst<T> c;
     axis_consts(a.ax[ax], c);
-    TileAxis<T>& A = AX[ax];
-    A.x_first = c.x_first; A.x_last = c.x_last; A.inv_h = c.inv_h;
-    A.period = T(fabs(p.period));
-    A.nk = a.ax[ax].nk; A.n = a.ax[ax].n;
-    int off = 0;
-    for (int k = 0; k < ax; ++k) off += 2 * a.ax[k].nk;
-    A.koff = off;
-    A.wrap = a.ax[ax].wrap; A.periodic = a.ax[ax].periodic;
-    A.chk_lo = !a.ax[ax].wrap && !p.keep_lo;
-    A.chk_hi = !a.ax[ax].wrap && !p.keep_hi;
-    A.order = p.derivative;
-    A.fill_lo = T(p.fill_lo); A.fill_hi = T(p.fill_hi);
+    AX[ax].x_first = c.x_first; AX[ax].inv_h = c.inv_h; AX[ax].x_last = c.x_last;
   }
+  if (DEVP && threadIdx.x == 32) params_s = *a.dp;
+  const ipx_params& P = DEVP ? params_s : a.hp;
   int knot_elems = 0;
 #pragma unroll
   for (int ax = 0; ax < ND; ++ax) {
@@ -252,31 +238,35 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
     T x0[ND], x1[ND], dxi[ND];
 #pragma unroll
     for (int ax = 0; ax < ND; ++ax) {
-      const TileAxis<T>& A = AX[ax];
+      const AxisDesc<T>& A = a.ax[ax];
       T q = qc[ax];
       if (A.wrap) {
-        const T P = A.period;
+        const T Pd = T(fabs(P.axis[ax].period));
         T r = q;
-        r = q < T(0) ? q + P : r;       // [-P,0): fmod leaves q, the sign fix adds P
-        r = q >= P ? q - P : r;         // [P,2P]: exact (Sterbenz)
-        if (!(q >= -P && q <= P + P)) r = py_mod(q, P);  // anything else: the exact remainder
+        r = q < T(0) ? q + Pd : r;      // [-P,0): fmod leaves q, the sign fix adds P
+        r = q >= Pd ? q - Pd : r;       // [P,2P]: exact (Sterbenz)
+        if (!(q >= -Pd && q <= Pd + Pd)) r = py_mod(q, Pd);  // anything else: the exact remainder
         q = r;
         qc[ax] = q;
       }
       const int nk = A.nk;
-      const T* ks = smT + A.koff;
-      int i = min(max(t_floor_to_int((q - A.x_first) * A.inv_h), 0), nk - 2) + 1;
+      int koff = 0;
+#pragma unroll
+      for (int k = 0; k < ax; ++k) koff += 2 * a.ax[k].nk;
+      const T* ks = smT + koff;
+      const T xf = AX[ax].x_first, ih = AX[ax].inv_h;
+      int i = min(max(t_floor_to_int((q - xf) * ih), 0), nk - 2) + 1;
       T lo = ks[i - 1], hi = ks[i];
       // exact check of the guess against the knots (NaN fails it); the rare miss re-searches
       if (!((q >= lo || i == 1) && (q < hi || i == nk - 1))) {
-        i = bin_index(ks, nk, q, A.x_first, A.inv_h, lo, hi);
+        i = bin_index(ks, nk, q, xf, ih, lo, hi);
       }
       li[ax] = i; x0[ax] = lo; x1[ax] = hi;
       dxi[ax] = ks[nk + i];
       if (A.periodic) {
         int s0 = i - 2; s0 += s0 < 0 ? A.n : 0;
         int s1 = i - 1; s1 -= s1 >= A.n ? A.n : 0;
-        const int32_t* pm = a.ax[ax].perm;
+        const int32_t* pm = A.perm;
         t0[ax] = pm ? pm[s0] : s0;
         t1[ax] = pm ? pm[s1] : s1;
       } else {
@@ -289,7 +279,7 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
     bool key_ok = true;  // 32-bit keys suffice unless the knot vectors are huge
 #pragma unroll
     for (int ax = 0; ax < ND - 1; ++ax) {
-      const unsigned m = (unsigned)AX[ax].nk + 1u;
+      const unsigned m = (unsigned)a.ax[ax].nk + 1u;
       key_ok = key_ok && ((unsigned long long)key * m < 0xffff0000ull);
       key = key * m + (unsigned)li[ax];
     }
@@ -320,7 +310,7 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
         for (int ax = 0; ax < ND - 1; ++ax) {
           const int c0 = __shfl_sync(0xffffffffu, t0[ax], ld);
           const int c1 = __shfl_sync(0xffffffffu, t1[ax], ld);
-          colnode = colnode * AX[ax].n + (((ccol >> ax) & 1) ? c1 : c0);
+          colnode = colnode * a.ax[ax].n + (((ccol >> ax) & 1) ? c1 : c0);
         }
         // table position of the first node of the run, if the run is contiguous in the table
         int zt0 = zmin;
@@ -349,7 +339,7 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
         if (!have_w) {
 #pragma unroll
           for (int ax = 0; ax < ND; ++ax)
-            hermite_weights_r(qc[ax], x0[ax], x1[ax], AX[ax].order, dxi[ax], w[ax]);
+            hermite_weights_r(qc[ax], x0[ax], x1[ax], P.axis[ax].derivative, dxi[ax], w[ax]);
           have_w = true;
         }
         cp_async_wait_all();
@@ -369,11 +359,11 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
       // ---- direct per-lane gather (incoherent queries) ----
 #pragma unroll
       for (int ax = 0; ax < ND; ++ax)
-        hermite_weights_r(qc[ax], x0[ax], x1[ax], AX[ax].order, dxi[ax], w[ax]);
+        hermite_weights_r(qc[ax], x0[ax], x1[ax], P.axis[ax].derivative, dxi[ax], w[ax]);
       res = contract_cubic<T, ND>(w, [&](int bits, T* r) {
         size_t node = (bits & 1) ? t1[0] : t0[0];
 #pragma unroll
-        for (int ax = 1; ax < ND; ++ax) node = node * AX[ax].n + (((bits >> ax) & 1) ? t1[ax] : t0[ax]);
+        for (int ax = 1; ax < ND; ++ax) node = node * a.ax[ax].n + (((bits >> ax) & 1) ? t1[ax] : t0[ax]);
         const T* p = reinterpret_cast<const T*>(tabc) + node * Cfg::NT;
         if (ND == 1) ldg_rec2(p, r);
         if (ND == 2) ldg_rec4(p, r);
@@ -385,9 +375,10 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
       // extrapolation fills, x then y then z, later axes win (_spline.py:1101-1103)
 #pragma unroll
       for (int ax = 0; ax < ND; ++ax) {
-        const TileAxis<T>& A = AX[ax];
-        if (A.chk_lo && qc[ax] < A.x_first) res = A.fill_lo;
-        if (A.chk_hi && qc[ax] > A.x_last) res = A.fill_hi;
+        if (a.ax[ax].wrap) continue;
+        const ipx_axis_params& pa = P.axis[ax];
+        if (!pa.keep_lo && qc[ax] < AX[ax].x_first) res = T(pa.fill_lo);
+        if (!pa.keep_hi && qc[ax] > AX[ax].x_last) res = T(pa.fill_hi);
       }
       a.out[qi] = res;
       if (want_idx) {
@@ -422,7 +413,7 @@ static bool launch_tile(const EvalArgs<T, ND>& a, cudaStream_t s) {
     for (int ax = 0; ax < ND; ++ax) total_knots += a.ax[ax].nk;
     if (total_knots > kSmemKnotCap) return false;
     const size_t smem = tile_smem_bytes<T, ND>(a);
-    auto kern = eval_tile_kernel<T, ND>;
+    auto kern = a.dp ? eval_tile_kernel<T, ND, true> : eval_tile_kernel<T, ND, false>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return false;
     int dev = 0, sms = 148, per_sm = 1;
