@@ -1,56 +1,51 @@
 // ipx_eval_tile.cuh -- warp-cooperative, shared-memory-staged evaluation of the cubic family
 // on AoS-packed tables (the Interpolator1D/2D/3D path).  Included by ipx_eval.cu.
 //
-// Why: a cubic query needs 2^d corner records (8 x 64 B in 3-D f64).  When every lane gathers
-// its own records, each 128-bit load instruction of a warp touches one cache line per distinct
-// cell in the warp and 32 such instructions are needed, so the L1 / LSU pipe, not HBM, bounds
-// the kernel (profiles/ncu_eval3d_r01_baseline.txt).  Spatially coherent (cell-sorted) queries
-// put a warp's 32 queries into a handful of consecutive cells along the fastest table axis.
-// The warp therefore
-//   1. groups its lanes by the cell "column" (interval indices on all axes but the last),
-//   2. cooperatively copies the run of nodes the group needs -- 2^(d-1) columns x (run+1)
-//      nodes, contiguous along the last axis -- global -> shared with full-line 128-bit
-//      accesses (each byte crosses L1 once per warp instead of once per lane),
-//   3. lets every lane read its 2^d records from shared memory (same-cell lanes broadcast),
-//      and run the separable Hermite contraction.
-// Incoherent queries (many groups in a warp) take the direct per-lane gather instead, which
-// has more memory-level parallelism; both paths compute the same arithmetic.
+// Why.  A cubic query needs 2^d corner records (8 x 64 B in 3-D f64 = 512 B of operands).
+// Delivering operands to registers costs one LSU wavefront per 128 B per warp no matter where
+// they come from (L1 or shared memory), so a thread-per-query gather is bound by the LSU/L1
+// pipe -- 4 cycles per query per SM in 3-D f64 -- long before HBM
+// (profiles/ncu_eval3d_r01_baseline.txt).  Spatially coherent (cell-sorted) queries put
+// neighbouring queries into the same or the next cell along the fastest table axis.  So:
+//   1. a warp takes 64 consecutive queries, two per lane;
+//   2. lanes are grouped by cell "column" (interval indices on all axes but the last);
+//   3. the group's run of nodes -- 2^(d-1) columns x (run+1) nodes, contiguous along the last
+//      axis -- is copied global -> shared with cp.async, full-line 128-bit accesses (each byte
+//      crosses L1 once per warp, not once per lane);
+//   4. every lane walks the run one node LAYER at a time (a layer = the 2^(d-1) records at one
+//      position of the last axis), reads each record from shared memory ONCE and applies it
+//      to both of its queries.  Two queries in the same cell share both layers, in adjacent
+//      cells one, so operand traffic per query drops by up to 2x;
+//   5. the contraction is separable and runs last-axis-last: per layer, contract the other
+//      axes into (value part, last-axis-slope part), then combine with the last-axis weights.
+// A second query that is not in its partner's cell or the one above it, and warps whose
+// queries are spread over many columns (incoherent order), use the same layer arithmetic on
+// the lane's own query with a direct gather, so a query's result never depends on which path
+// served it (tests/test_gpu_parity.py::test_full_size_properties_c4 checks bitwise invariance
+// under permutation of the queries).
 //
-// Knot vectors and reciprocal cell widths are staged in shared memory once per CTA (the
-// grid is persistent), so the interval lookup and the local coordinate cost no global loads
-// and no divisions per query.  1/dx is computed by the same IEEE division the direct path
-// uses, so results are bit-identical between the two.
+// Knot vectors and reciprocal cell widths are staged in shared memory once per CTA (the grid
+// is persistent): the interval lookup costs no global loads and the local coordinate no
+// division per query.  1/dx is produced by the same IEEE division as in the generic kernel.
 #pragma once
 
 namespace ipx {
 
 constexpr int kTileThreads = 256;
 constexpr int kTileWarps = kTileThreads / 32;
-constexpr int kRunCap = 16;       // nodes of one run held per column
-constexpr int kMaxGroups = 4;     // more distinct columns than this in a warp -> direct path
+constexpr int kRunCap = 16;         // nodes of one run held per column
+constexpr int kMaxGroups = 4;       // more distinct columns than this in a warp -> direct path
 constexpr int kSmemKnotCap = 3072;  // total knots (all axes) staged in shared memory
 
 template <typename T, int ND> struct TileCfg {
   static constexpr int NT = 1 << ND;                       // values per record
   static constexpr int NC = 1 << (ND - 1);                 // columns per group
+  static constexpr int NCA = ND > 1 ? ND - 1 : 1;          // column axes (array extent)
   static constexpr int REC_BYTES = NT * (int)sizeof(T);
   static constexpr int CH = REC_BYTES / 16;                // 16-byte chunks per record
   static constexpr int STRIDE = REC_BYTES + (REC_BYTES >= 32 ? 16 : 0);  // bank-conflict padding
   static constexpr int WARP_TILE_BYTES = NC * kRunCap * STRIDE;
 };
-
-// wrap for a positive period with fast exact paths around the principal interval:
-//   [0,P): q     [-P,0): q+P (what fmod + sign fix gives)     [P,2P]: q-P (exact, Sterbenz)
-template <typename T> __device__ __forceinline__ T py_mod_fast(T q, T P) {
-  if (q >= T(0)) {
-    if (q < P) return q;
-    if (q <= P + P) return q - P;
-  } else if (q >= -P) {
-    T r = q + P;  // fmod(q,P) == q here, then the sign fix adds P
-    return r;
-  }
-  return py_mod(q, P);
-}
 
 // cubic Hermite weights from the local coordinate pieces (same formulas as hermite_weights)
 template <typename T>
@@ -88,66 +83,74 @@ template <typename T, int NT> __device__ __forceinline__ void lds_record(const c
   }
 }
 
-// separable contraction with a record loader: load(corner_bits, r) fills the 2^ND values of
-// the node at corner bits (bit ax = upper corner along axis ax), canonical record order.
-template <typename T, int ND, typename Loader>
-__device__ __forceinline__ T contract_cubic(const T (*w)[4], Loader load) {
-  T res = T(0);
+template <typename T, int NT> __device__ __forceinline__ void ldg_record(const T* p, T* r) {
+  if (NT == 2) ldg_rec2(p, r);
+  if (NT == 4) ldg_rec4(p, r);
+  if (NT == 8) ldg_rec8(p, r);
+}
+
+// weights of NQ queries that walk a layer together
+template <typename T, int ND, int NQ> struct WeightRefs {
+  const T (*w[NQ])[4];
+};
+
+// One layer of the separable contraction, for NQ queries that share the layer's records.
+// load(c, r) fills the record of column c (bit ax of c = upper corner along column axis ax) in
+// canonical order (last axis fastest).  On return A[k][0] is the layer's value part and
+// A[k][1] its last-axis-slope part for query k.
+template <typename T, int ND, int NQ, typename Loader>
+__device__ __forceinline__ void layer_contract(Loader load, const WeightRefs<T, ND, NQ>& W, T (&A)[NQ][2]) {
   if (ND == 1) {
+    T r[2];
+    load(0, r);
 #pragma unroll
-    for (int ii = 0; ii < 2; ++ii) {
-      T r[2];
-      load(ii, r);
-      res = fma(r[1], w[0][2 + ii], fma(r[0], w[0][ii], res));
-    }
+    for (int k = 0; k < NQ; ++k) { A[k][0] = r[0]; A[k][1] = r[1]; }
   } else if (ND == 2) {
 #pragma unroll
-    for (int ii = 0; ii < 2; ++ii) {
-      T p[2] = {T(0), T(0)};
+    for (int k = 0; k < NQ; ++k) { A[k][0] = T(0); A[k][1] = T(0); }
 #pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        T r[4];
-        load(ii | (jj << 1), r);
-        p[0] = fma(r[1], w[1][2 + jj], fma(r[0], w[1][jj], p[0]));
-        p[1] = fma(r[3], w[1][2 + jj], fma(r[2], w[1][jj], p[1]));
+    for (int ii = 0; ii < 2; ++ii) {
+      T r[4];  // [f, fy, fx, fxy]: index = (d/dy) + 2 (d/dx)
+      load(ii, r);
+#pragma unroll
+      for (int k = 0; k < NQ; ++k) {
+        A[k][0] = fma(r[2], W.w[k][0][2 + ii], fma(r[0], W.w[k][0][ii], A[k][0]));
+        A[k][1] = fma(r[3], W.w[k][0][2 + ii], fma(r[1], W.w[k][0][ii], A[k][1]));
       }
-      res = fma(p[1], w[0][2 + ii], fma(p[0], w[0][ii], res));
     }
   } else {
 #pragma unroll
+    for (int k = 0; k < NQ; ++k) { A[k][0] = T(0); A[k][1] = T(0); }
+#pragma unroll
     for (int ii = 0; ii < 2; ++ii) {
-      T v[2] = {T(0), T(0)};
+      T u[NQ][4];  // index = (d/dz) + 2 (d/dx), y contracted
+#pragma unroll
+      for (int k = 0; k < NQ; ++k) { u[k][0] = T(0); u[k][1] = T(0); u[k][2] = T(0); u[k][3] = T(0); }
 #pragma unroll
       for (int jj = 0; jj < 2; ++jj) {
-        T p[4] = {T(0), T(0), T(0), T(0)};
+        T r[8];  // [f, fz, fy, fyz, fx, fxz, fxy, fxyz]: index = (d/dz) + 2 (d/dy) + 4 (d/dx)
+        load(ii | (jj << 1), r);
 #pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-          T r[8];
-          load(ii | (jj << 1) | (kk << 2), r);
+        for (int k = 0; k < NQ; ++k) {
 #pragma unroll
-          for (int m = 0; m < 4; ++m)
-            p[m] = fma(r[2 * m + 1], w[2][2 + kk], fma(r[2 * m], w[2][kk], p[m]));
+          for (int m = 0; m < 4; ++m) {
+            const int src = (m & 1) + 4 * (m >> 1);
+            u[k][m] = fma(r[src + 2], W.w[k][1][2 + jj], fma(r[src], W.w[k][1][jj], u[k][m]));
+          }
         }
-        v[0] = fma(p[1], w[1][2 + jj], fma(p[0], w[1][jj], v[0]));
-        v[1] = fma(p[3], w[1][2 + jj], fma(p[2], w[1][jj], v[1]));
       }
-      res = fma(v[1], w[0][2 + ii], fma(v[0], w[0][ii], res));
+#pragma unroll
+      for (int k = 0; k < NQ; ++k) {
+        A[k][0] = fma(u[k][2], W.w[k][0][2 + ii], fma(u[k][0], W.w[k][0][ii], A[k][0]));
+        A[k][1] = fma(u[k][3], W.w[k][0][2 + ii], fma(u[k][1], W.w[k][0][ii], A[k][1]));
+      }
     }
   }
-  return res;
 }
 
 // table index of knot position p along the LAST axis (run axis)
 template <typename T> __device__ __forceinline__ int run_table_index(const AxisDesc<T>& A, int p) {
   return padded_to_table(A, p);
-}
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.wait_all;\n" ::: "memory");
 }
 
 // knot-derived constants of one axis (need device data, so they live in shared memory);
@@ -156,8 +159,24 @@ template <typename T> struct TileAxis {
   T x_first, inv_h, x_last, pad;
 };
 
+// one located query: weights formed, indices kept
+template <typename T, int ND> struct QState {
+  T w[ND][4];
+  int li[ND];                      // interval index per axis
+  int t0[TileCfg<T, ND>::NCA];     // column-axis corner table indices
+  int t1[TileCfg<T, ND>::NCA];
+  unsigned fill;                   // bit 2ax: q < knots[0], bit 2ax+1: q > knots[-1] (axes that fill)
+};
+
+__device__ __forceinline__ void cp_async16_s(unsigned smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+}
+
 template <typename T, int ND, bool DEVP>
-__global__ void __launch_bounds__(kTileThreads, 3)
+__global__ void __launch_bounds__(kTileThreads, 2)
 eval_tile_kernel(const EvalArgs<T, ND> a) {
   using Cfg = TileCfg<T, ND>;
   constexpr int LPC = 32 / Cfg::NC;          // lanes that copy one column
@@ -165,10 +184,10 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
   static_assert(LPC % Cfg::CH == 0 && NPR >= 1, "column copy layout");
   extern __shared__ __align__(16) char smem[];
   __shared__ TileAxis<T> AX[ND];
+  __shared__ ipx_params params_s;  // only used when the traced operands live in device memory
   T* const smT = reinterpret_cast<T*>(smem);
 
   // ---- per-CTA staging: axis constants, traced operands, knots and reciprocal widths ----
-  __shared__ ipx_params params_s;  // only used when the traced operands live in device memory
   if (threadIdx.x < ND) {
     const int ax = threadIdx.x;
     AxisConst<T> c;
@@ -206,40 +225,16 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
   const int cl = lane - ccol * LPC;
   const int cnode0 = cl / Cfg::CH;
   const int cpart = cl - cnode0 * Cfg::CH;
-  const unsigned cdst0 = (unsigned)__cvta_generic_to_shared(tile) +
-                         (ccol * kRunCap + cnode0) * Cfg::STRIDE + 16 * cpart;
+  const unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);
+  const unsigned cdst0 = tile_s + (ccol * kRunCap + cnode0) * Cfg::STRIDE + 16 * cpart;
 
-  const int64_t step = (int64_t)gridDim.x * kTileThreads;
-  const int64_t q0 = (int64_t)blockIdx.x * kTileThreads + (threadIdx.x & ~31);  // warp's first query
-  if (q0 >= a.nq) return;  // whole warp idle (after the CTA barrier above)
-  const int rounds = (int)((a.nq - q0 + step - 1) / step);
-
-  // software prefetch of the query stream: the loads for the next round are in flight while
-  // this round gathers and contracts
-  int64_t qi = q0 + lane;
-  T qn[ND];
-#pragma unroll
-  for (int ax = 0; ax < ND; ++ax) qn[ax] = qi < a.nq ? a.ax[ax].q[qi] : T(0);
-
-  for (int round = 0; round < rounds; ++round, qi += step) {
-    const bool active = qi < a.nq;
-    T qc[ND];
-#pragma unroll
-    for (int ax = 0; ax < ND; ++ax) qc[ax] = qn[ax];
-    {
-      const int64_t qnext = qi + step;
-      const bool more = qnext < a.nq;
-#pragma unroll
-      for (int ax = 0; ax < ND; ++ax) qn[ax] = more ? a.ax[ax].q[qnext] : T(0);
-    }
-
-    // ---- locate: wrap, interval lookup in shared memory, corner indices ----
-    int li[ND], t0[ND], t1[ND];
-    T x0[ND], x1[ND], dxi[ND];
+  // ---- one located query -------------------------------------------------------------
+  auto locate_q = [&](const T (&qraw)[ND], QState<T, ND>& S, int& pz) {
+    S.fill = 0;
 #pragma unroll
     for (int ax = 0; ax < ND; ++ax) {
       const AxisDesc<T>& A = a.ax[ax];
-      T q = qc[ax];
+      T q = qraw[ax];
       if (A.wrap) {
         const T Pd = T(fabs(P.axis[ax].period));
         T r = q;
@@ -247,7 +242,6 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
         r = q >= Pd ? q - Pd : r;       // [P,2P]: exact (Sterbenz)
         if (!(q >= -Pd && q <= Pd + Pd)) r = py_mod(q, Pd);  // anything else: the exact remainder
         q = r;
-        qc[ax] = q;
       }
       const int nk = A.nk;
       int koff = 0;
@@ -261,55 +255,158 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
       if (!((q >= lo || i == 1) && (q < hi || i == nk - 1))) {
         i = bin_index(ks, nk, q, xf, ih, lo, hi);
       }
-      li[ax] = i; x0[ax] = lo; x1[ax] = hi;
-      dxi[ax] = ks[nk + i];
-      if (A.periodic) {
-        int s0 = i - 2; s0 += s0 < 0 ? A.n : 0;
-        int s1 = i - 1; s1 -= s1 >= A.n ? A.n : 0;
-        const int32_t* pm = A.perm;
-        t0[ax] = pm ? pm[s0] : s0;
-        t1[ax] = pm ? pm[s1] : s1;
-      } else {
-        t0[ax] = i - 1; t1[ax] = i;
+      S.li[ax] = i;
+      hermite_weights_r(q, lo, hi, P.axis[ax].derivative, ks[nk + i], S.w[ax]);
+      if (!A.wrap) {
+        const ipx_axis_params& pa = P.axis[ax];
+        if (!pa.keep_lo && q < xf) S.fill |= 1u << (2 * ax);
+        if (!pa.keep_hi && q > AX[ax].x_last) S.fill |= 2u << (2 * ax);
+      }
+      if (ax < ND - 1) {
+        if (A.periodic) {
+          int s0 = i - 2; s0 += s0 < 0 ? A.n : 0;
+          int s1 = i - 1; s1 -= s1 >= A.n ? A.n : 0;
+          const int32_t* pm = A.perm;
+          S.t0[ax] = pm ? pm[s0] : s0;
+          S.t1[ax] = pm ? pm[s1] : s1;
+        } else {
+          S.t0[ax] = i - 1; S.t1[ax] = i;
+        }
       }
     }
+    pz = S.li[ND - 1] - 1;
+  };
 
-    // ---- group lanes by cell column (all axes but the last) ----
+  auto column_key = [&](const QState<T, ND>& S, bool& ok) {
     unsigned key = 0;
-    bool key_ok = true;  // 32-bit keys suffice unless the knot vectors are huge
 #pragma unroll
     for (int ax = 0; ax < ND - 1; ++ax) {
       const unsigned m = (unsigned)a.ax[ax].nk + 1u;
-      key_ok = key_ok && ((unsigned long long)key * m < 0xffff0000ull);
-      key = key * m + (unsigned)li[ax];
+      ok = ok && ((unsigned long long)key * m < 0xffff0000ull);
+      key = key * m + (unsigned)S.li[ax];
     }
-    if (!active) key = 0xffffffffu;
-    const unsigned same = __match_any_sync(0xffffffffu, key);
-    const unsigned leaders = __ballot_sync(0xffffffffu, ((__ffs(same) - 1) == lane) && active);
-    const int pz = li[ND - 1] - 1;  // lower knot position on the run axis
+    return key;
+  };
+
+  // combine a layer with the run-axis weights of corner `kk` (0 = lower node, 1 = upper)
+  auto finish_layer = [&](const QState<T, ND>& S, const T (&A)[2], int kk, T acc) {
+    return fma(A[0], S.w[ND - 1][kk], fma(A[1], S.w[ND - 1][2 + kk], acc));
+  };
+
+  // direct per-lane gather of one query (incoherent queries, second queries that cannot ride)
+  auto eval_direct = [&](const QState<T, ND>& S, int pz) {
+    T res = T(0);
+    WeightRefs<T, ND, 1> W;
+    W.w[0] = S.w;
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      const int zt = run_table_index(RA, pz + kk);
+      T A[1][2];
+      layer_contract<T, ND, 1>(
+          [&](int c, T* r) {
+            size_t node = 0;
+#pragma unroll
+            for (int ax = 0; ax < ND - 1; ++ax) node = node * a.ax[ax].n + (((c >> ax) & 1) ? S.t1[ax] : S.t0[ax]);
+            node = node * RA.n + zt;
+            ldg_record<T, Cfg::NT>(reinterpret_cast<const T*>(tabc) + node * Cfg::NT, r);
+          },
+          W, A);
+      res = finish_layer(S, A[0], kk, res);
+    }
+    return res;
+  };
+
+  auto store_q = [&](const QState<T, ND>& S, int64_t qi, T res) {
+    // extrapolation fills, x then y then z, later axes win (_spline.py:1101-1103)
+    if (S.fill) {
+#pragma unroll
+      for (int ax = 0; ax < ND; ++ax) {
+        if (S.fill & (1u << (2 * ax))) res = T(P.axis[ax].fill_lo);
+        if (S.fill & (2u << (2 * ax))) res = T(P.axis[ax].fill_hi);
+      }
+    }
+    a.out[qi] = res;
+    if (want_idx) {
+#pragma unroll
+      for (int ax = 0; ax < ND; ++ax) a.idx_out[(int64_t)ax * a.nq + qi] = S.li[ax];
+    }
+  };
+
+  // ---- persistent loop: 64 consecutive queries per warp per round ------------------------
+  const int64_t step = (int64_t)gridDim.x * kTileThreads * 2;
+  const int64_t w0 = ((int64_t)blockIdx.x * kTileWarps + warp) * 64;  // warp's first query
+  if (w0 >= a.nq) return;  // whole warp idle (after the CTA barrier above)
+  const int rounds = (int)((a.nq - w0 + step - 1) / step);
+
+  int64_t qa = w0 + 2 * lane;  // this lane's first query; its second is qa + 1
+  T qn[2][ND];
+  auto prefetch = [&](int64_t q) {
+#pragma unroll
+    for (int ax = 0; ax < ND; ++ax) {
+      if (q + 1 < a.nq) {  // q is even and the arrays are 16-byte aligned: one vector load
+        if (sizeof(T) == 8) {
+          const double2 v = *reinterpret_cast<const double2*>(a.ax[ax].q + q);
+          qn[0][ax] = T(v.x); qn[1][ax] = T(v.y);
+        } else {
+          const float2 v = *reinterpret_cast<const float2*>(a.ax[ax].q + q);
+          qn[0][ax] = T(v.x); qn[1][ax] = T(v.y);
+        }
+      } else {
+        qn[0][ax] = q < a.nq ? a.ax[ax].q[q] : T(0);
+        qn[1][ax] = T(0);
+      }
+    }
+  };
+  prefetch(qa);
+
+  for (int round = 0; round < rounds; ++round, qa += step) {
+    const bool act_a = qa < a.nq;
+    const bool act_b = qa + 1 < a.nq;
+    T qc[2][ND];
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+      for (int ax = 0; ax < ND; ++ax) qc[k][ax] = qn[k][ax];
+    if (round + 1 < rounds) prefetch(qa + step);
+
+    QState<T, ND> Sa, Sb;
+    int pza, pzb;
+    locate_q(qc[0], Sa, pza);
+    locate_q(qc[1], Sb, pzb);
+
+    bool key_ok = true;
+    unsigned ka = column_key(Sa, key_ok);
+    const unsigned kb = column_key(Sb, key_ok);
+    // b rides with a if it is in a's cell or the next one up the run axis
+    const int dz = pzb - pza;
+    const bool ride = act_b && kb == ka && (dz == 0 || dz == 1);
+    const bool same = dz == 0;
+    if (!act_a) ka = 0xffffffffu;
+    const unsigned mates = __match_any_sync(0xffffffffu, ka);
+    const unsigned leaders = __ballot_sync(0xffffffffu, ((__ffs(mates) - 1) == lane) && act_a);
     const bool coherent = key_ok && __popc(leaders) <= kMaxGroups;
 
-    T w[ND][4];
-    T res = T(0);
+    T res_a = T(0), res_b = T(0);
+    bool done_b = !act_b;
     if (coherent) {
-      unsigned todo = __ballot_sync(0xffffffffu, active);
-      bool have_w = false;
+      const int ptop = ride ? pzb : pza;  // highest cell this lane touches in the group pass
+      unsigned todo = __ballot_sync(0xffffffffu, act_a);
       while (todo) {
         const int ld = __ffs(todo) - 1;
-        const unsigned grp = __shfl_sync(0xffffffffu, same, ld) & todo;
+        const unsigned grp = __shfl_sync(0xffffffffu, mates, ld) & todo;
         const bool in_grp = (grp >> lane) & 1u;
-        const int zmin = __reduce_min_sync(0xffffffffu, in_grp ? pz : 0x7fffffff);
-        const bool sub = in_grp && (pz - zmin) <= kRunCap - 2;
+        const int zmin = __reduce_min_sync(0xffffffffu, in_grp ? pza : 0x7fffffff);
+        const bool sub = in_grp && (ptop - zmin) <= kRunCap - 2;
         const unsigned subm = __ballot_sync(0xffffffffu, sub);
-        const int zmax = __reduce_max_sync(0xffffffffu, sub ? pz : -0x7fffffff);
+        const int zmax = __reduce_max_sync(0xffffffffu, sub ? ptop : -0x7fffffff);
         const int extent = zmax - zmin + 2;  // nodes per column, <= kRunCap
 
         // node index of (this lane's copy column, run position 0), from the leader's corners
         int colnode = 0;
 #pragma unroll
         for (int ax = 0; ax < ND - 1; ++ax) {
-          const int c0 = __shfl_sync(0xffffffffu, t0[ax], ld);
-          const int c1 = __shfl_sync(0xffffffffu, t1[ax], ld);
+          const int c0 = __shfl_sync(0xffffffffu, Sa.t0[ax], ld);
+          const int c1 = __shfl_sync(0xffffffffu, Sa.t1[ax], ld);
           colnode = colnode * a.ax[ax].n + (((ccol >> ax) & 1) ? c1 : c0);
         }
         // table position of the first node of the run, if the run is contiguous in the table
@@ -324,68 +421,67 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
           const char* src = tabc + ((size_t)colnode * RA.n + zt0) * Cfg::REC_BYTES + 16 * cl;
           unsigned dst = cdst0;
           for (int node = cnode0; node < extent; node += NPR) {
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+            cp_async16_s(dst, src);
             src += NPR * Cfg::REC_BYTES;
             dst += NPR * Cfg::STRIDE;
           }
         } else {
           for (int node = cnode0; node < extent; node += NPR) {
             const int zt = run_table_index(RA, zmin + node);
-            cp_async16(tile + (ccol * kRunCap + node) * Cfg::STRIDE + 16 * cpart,
-                       tabc + ((size_t)colnode * RA.n + zt) * Cfg::REC_BYTES + 16 * cpart);
+            cp_async16_s(tile_s + (ccol * kRunCap + node) * Cfg::STRIDE + 16 * cpart,
+                         tabc + ((size_t)colnode * RA.n + zt) * Cfg::REC_BYTES + 16 * cpart);
           }
-        }
-        // the Hermite weights do not depend on the table: compute them under the copy
-        if (!have_w) {
-#pragma unroll
-          for (int ax = 0; ax < ND; ++ax)
-            hermite_weights_r(qc[ax], x0[ax], x1[ax], P.axis[ax].derivative, dxi[ax], w[ax]);
-          have_w = true;
         }
         cp_async_wait_all();
         __syncwarp();
         if (sub) {
-          const char* rec0 = tile + (pz - zmin) * Cfg::STRIDE;
-          res = contract_cubic<T, ND>(w, [&](int bits, T* r) {
-            const int c = bits & (Cfg::NC - 1);
-            const int kk = bits >> (ND - 1);
-            lds_record<T, Cfg::NT>(rec0 + (c * kRunCap + kk) * Cfg::STRIDE, r);
-          });
+          const char* lay = tile + (pza - zmin) * Cfg::STRIDE;  // layer of a's lower node
+          auto tile_loader = [](const char* base) {
+            return [base](int c, T* r) { lds_record<T, Cfg::NT>(base + c * (kRunCap * Cfg::STRIDE), r); };
+          };
+          if (ride) {
+            WeightRefs<T, ND, 2> W2;
+            W2.w[0] = Sa.w;
+            W2.w[1] = Sb.w;
+            T A[2][2];
+            // layer 0: lower node of a's cell (and of b's, if b shares the cell)
+            layer_contract<T, ND, 2>(tile_loader(lay), W2, A);
+            res_a = finish_layer(Sa, A[0], 0, T(0));
+            if (same) res_b = finish_layer(Sb, A[1], 0, T(0));
+            // layer 1: upper node of a's cell = upper (same cell) or lower (next cell) node of b's
+            layer_contract<T, ND, 2>(tile_loader(lay + Cfg::STRIDE), W2, A);
+            res_a = finish_layer(Sa, A[0], 1, res_a);
+            res_b = same ? finish_layer(Sb, A[1], 1, res_b) : finish_layer(Sb, A[1], 0, T(0));
+            if (!same) {
+              // layer 2: upper node of b's cell
+              WeightRefs<T, ND, 1> W1;
+              W1.w[0] = Sb.w;
+              T B[1][2];
+              layer_contract<T, ND, 1>(tile_loader(lay + 2 * Cfg::STRIDE), W1, B);
+              res_b = finish_layer(Sb, B[0], 1, res_b);
+            }
+            done_b = true;
+          } else {
+            WeightRefs<T, ND, 1> W1;
+            W1.w[0] = Sa.w;
+            T A[1][2];
+            layer_contract<T, ND, 1>(tile_loader(lay), W1, A);
+            res_a = finish_layer(Sa, A[0], 0, T(0));
+            layer_contract<T, ND, 1>(tile_loader(lay + Cfg::STRIDE), W1, A);
+            res_a = finish_layer(Sa, A[0], 1, res_a);
+          }
         }
         __syncwarp();
         todo &= ~subm;
       }
-    } else if (active) {
-      // ---- direct per-lane gather (incoherent queries) ----
-#pragma unroll
-      for (int ax = 0; ax < ND; ++ax)
-        hermite_weights_r(qc[ax], x0[ax], x1[ax], P.axis[ax].derivative, dxi[ax], w[ax]);
-      res = contract_cubic<T, ND>(w, [&](int bits, T* r) {
-        size_t node = (bits & 1) ? t1[0] : t0[0];
-#pragma unroll
-        for (int ax = 1; ax < ND; ++ax) node = node * a.ax[ax].n + (((bits >> ax) & 1) ? t1[ax] : t0[ax]);
-        const T* p = reinterpret_cast<const T*>(tabc) + node * Cfg::NT;
-        if (ND == 1) ldg_rec2(p, r);
-        if (ND == 2) ldg_rec4(p, r);
-        if (ND == 3) ldg_rec8(p, r);
-      });
+    } else if (act_a) {
+      res_a = eval_direct(Sa, pza);
     }
+    // second queries that did not ride (other column, or further than one cell away)
+    if (!done_b) res_b = eval_direct(Sb, pzb);
 
-    if (active) {
-      // extrapolation fills, x then y then z, later axes win (_spline.py:1101-1103)
-#pragma unroll
-      for (int ax = 0; ax < ND; ++ax) {
-        if (a.ax[ax].wrap) continue;
-        const ipx_axis_params& pa = P.axis[ax];
-        if (!pa.keep_lo && qc[ax] < AX[ax].x_first) res = T(pa.fill_lo);
-        if (!pa.keep_hi && qc[ax] > AX[ax].x_last) res = T(pa.fill_hi);
-      }
-      a.out[qi] = res;
-      if (want_idx) {
-#pragma unroll
-        for (int ax = 0; ax < ND; ++ax) a.idx_out[(int64_t)ax * a.nq + qi] = li[ax];
-      }
-    }
+    if (act_a) store_q(Sa, qa, res_a);
+    if (act_b) store_q(Sb, qa + 1, res_b);
   }
 }
 
@@ -402,16 +498,20 @@ template <typename T, int ND> constexpr bool tile_supported() {
   return (1 << ND) * (int)sizeof(T) >= 16;
 }
 
-// Launches the tile kernel if it applies (record >= 16 B, knot vectors fit in shared memory);
-// returns false if the caller should use the generic kernel instead.
+// Launches the tile kernel if it applies (record >= 16 B, knot vectors fit in shared memory,
+// query arrays 16-byte aligned); returns false if the caller should use the generic kernel.
 template <typename T, int ND>
 static bool launch_tile(const EvalArgs<T, ND>& a, cudaStream_t s) {
   if constexpr (!tile_supported<T, ND>()) {
     return false;
   } else {
     int total_knots = 0;
-    for (int ax = 0; ax < ND; ++ax) total_knots += a.ax[ax].nk;
+    for (int ax = 0; ax < ND; ++ax) {
+      total_knots += a.ax[ax].nk;
+      if ((reinterpret_cast<uintptr_t>(a.ax[ax].q) & 15) != 0) return false;
+    }
     if (total_knots > kSmemKnotCap) return false;
+    if ((reinterpret_cast<uintptr_t>(a.tab[0]) & 15) != 0) return false;
     const size_t smem = tile_smem_bytes<T, ND>(a);
     auto kern = a.dp ? eval_tile_kernel<T, ND, true> : eval_tile_kernel<T, ND, false>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -421,7 +521,7 @@ static bool launch_tile(const EvalArgs<T, ND>& a, cudaStream_t s) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, smem);
     if (per_sm < 1) per_sm = 1;
-    int64_t need = (a.nq + kTileThreads - 1) / kTileThreads;
+    int64_t need = (a.nq + 2 * kTileThreads - 1) / (2 * kTileThreads);
     int64_t grid = (int64_t)sms * per_sm;  // persistent: one resident wave
     if (need < grid) grid = need;
     kern<<<(int)grid, kTileThreads, smem, s>>>(a);
