@@ -409,7 +409,9 @@ def run_ours(args):
     prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get("eval3d_f64_aos_sorted_bytes_per_launch")
+            traffic = json.load(open(prof)).get("eval3d_%s_sorted_1e8_bytes_per_launch" % args.dtype)
+            if nq != 100_000_000 or n != 256:
+                traffic = None  # the capture is of the default workload only
         except Exception:
             traffic = None
 
@@ -436,7 +438,7 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": ach_sorted, "peak": peak, "unit": "GB/s",
                      "frac": ach_sorted / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": bytes_launch,
-                     "kernel": "ipx::eval_kernel<double,3,CUBIC,AOS>"},
+                     "kernel": "ipx::eval_tile_kernel<%s,3>" % ("double" if args.dtype == "f64" else "float")},
         "random_order": {"value": world * nq / (ms_random * 1e-3), "ms_per_step": ms_random,
                          "roofline_frac": ach_random / peak,
                          "note": "random queries on a 1.07 GB table are bound by DRAM sector traffic "
