@@ -197,6 +197,7 @@ def cpu_step(knots, arrs, q):
 def cpu_measure(args, steps, warmup):
     from oracle import interpax_c as OC
 
+    OC.use_all_threads()
     knots, arrs = cpu_setup(args)
     q = cpu_queries(args.cpu_sample, SEED + 1)
     for _ in range(max(1, warmup)):

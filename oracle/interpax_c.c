@@ -65,6 +65,15 @@ static void build_matrices(void) {
   built = 1;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the baseline wants every host thread it can use */
+void ipxo_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int ipxo_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -35,6 +35,16 @@ def num_threads() -> int:
     return int(load().ipxo_num_threads())
 
 
+def use_all_threads() -> int:
+    """Use every host thread this process may run on (ignores OMP_NUM_THREADS=1 from torchrun)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    load().ipxo_set_threads(C.c_int(n))
+    return num_threads()
+
+
 def _ex(extrap, n):
     e6 = O._parse_extrap(extrap, n)
     arr = (Extrap * n)()

@@ -1,0 +1,165 @@
+"""Throughput of the other BASELINE.json configs (C1, C2, C3, C5) on one B200, with a parity
+spot-check of each against the oracle.  bench.py measures the headline config (C4); this
+script is the evidence for the rest.  Writes one JSON object per config to stdout.
+
+    python profiles/bench_configs.py [c1] [c2] [c3] [c5]
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import interpax_b200 as ipx  # noqa: E402
+from oracle import interpax_np as O  # noqa: E402  (checker only)
+
+dev = torch.device("cuda")
+PEAK = 6540.8
+if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+
+
+def timed(fn, steps=10, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def parity(got, want, rtol):
+    got, want = np.asarray(got), np.asarray(want)
+    fin = np.isfinite(want)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    err = float(np.max(np.abs(got[fin] - want[fin])) / np.max(np.abs(want[fin])))
+    return {"max_err_over_max_abs": err, "ok": bool(err <= rtol)}
+
+
+def c1():
+    xp = np.linspace(0, 2 * np.pi, 100)
+    xq = np.linspace(0, 2 * np.pi, 10000)
+    fp = np.sin(xp)
+    xpt, xqt, fpt = (torch.from_numpy(a).to(dev) for a in (xp, xq, fp))
+    ip = ipx.Interpolator1D(xpt, fpt, "cubic")
+    ms_f = timed(lambda: ipx.interp1d(xqt, xpt, fpt, method="cubic"), 50, 10)
+    ms_c = timed(lambda: ip(xqt), 50, 10)
+    got = ipx.interp1d(xq, xp, fp, method="cubic")
+    return {"config": "C1 README interp1d cubic, 100 knots, 1e4 queries, f64",
+            "us_per_call_functional": ms_f * 1e3, "us_per_call_class": ms_c * 1e3,
+            "max_err_vs_sin": float(np.abs(got - np.sin(xq)).max()),
+            "parity": parity(got, O.interp1d(xq, xp, fp, method="cubic"), 1e-12)}
+
+
+def c2():
+    out = []
+    n, B = 1_000_000, 64
+    g = torch.Generator(device=dev).manual_seed(1236)
+    x = torch.linspace(0, 1, n, dtype=torch.float64, device=dev)
+    fp = torch.randn((n, B), dtype=torch.float64, device=dev, generator=g)
+    nq = 1 << 23  # per chunk; 1e9 queries = 120 such chunks streamed through one 4.3 GB buffer
+    xq = torch.rand(nq, dtype=torch.float64, device=dev, generator=g) * 1.02 - 0.01
+    xs = torch.sort(xq).values
+    obuf = torch.empty((nq, B), dtype=torch.float64, device=dev)
+    for method in ("linear", "cubic2", "monotonic", "akima"):
+        t0 = time.perf_counter()
+        ip = ipx.Interpolator1D(x, fp, method)
+        torch.cuda.synchronize()
+        t_build = time.perf_counter() - t0
+        ms_r = timed(lambda: ip(xq, out=obuf), 5, 2)
+        ms_s = timed(lambda: ip(xs, out=obuf), 5, 2)
+        bytes_ = nq * (8 + 8 * B) + (1 if method == "linear" else 2) * n * B * 8 + n * 8
+        m = 1 << 12
+        got = ip(xq[:m]).cpu().numpy()
+        want = O.interp1d(xq[:m].cpu().numpy(), x.cpu().numpy(), fp.cpu().numpy(), method=method)
+        out.append({"config": f"C2 interp1d {method}, 1e6 knots, fp (1e6,64), 2^23-query chunk, f64",
+                    "queries_per_s_random": nq / ms_r * 1e3, "queries_per_s_sorted": nq / ms_s * 1e3,
+                    "roofline_frac_random": bytes_ / (ms_r * 1e-3) / 1e9 / PEAK,
+                    "roofline_frac_sorted": bytes_ / (ms_s * 1e-3) / 1e9 / PEAK,
+                    "slopes_precompute_s": t_build, "parity": parity(got, want, 1e-12)})
+        del ip
+    return out
+
+
+def c3():
+    n = 2048
+    g = torch.Generator(device=dev).manual_seed(1237)
+    x = torch.linspace(0, 1, n, dtype=torch.float64, device=dev)
+    f = torch.randn((n, n), dtype=torch.float64, device=dev, generator=g)
+    ip = ipx.Interpolator2D(x, x, f, "cubic", False)
+    nq = 250_000_000
+    xq = torch.rand(nq, dtype=torch.float64, device=dev, generator=g) * 1.02 - 0.01
+    yq = torch.rand(nq, dtype=torch.float64, device=dev, generator=g) * 1.02 - 0.01
+    key = (xq.clamp(0, 1) * (n - 1)).floor().long() * n + (yq.clamp(0, 1) * (n - 1)).floor().long()
+    o = torch.argsort(key)
+    del key
+    xs, ys = xq[o], yq[o]
+    del o
+    obuf = torch.empty(nq, dtype=torch.float64, device=dev)
+    res = []
+    bytes_ = nq * 24 + 4 * n * n * 8
+    for d in ((0, 0), (1, 0)):
+        ms_r = timed(lambda: ip(xq, yq, *d, out=obuf), 5, 2)
+        ms_s = timed(lambda: ip(xs, ys, *d, out=obuf), 5, 2)
+        m = 1 << 12
+        got = ip(xq[:m], yq[:m], *d).cpu().numpy()
+        want = O.Interpolator2D(x.cpu().numpy(), x.cpu().numpy(), f.cpu().numpy(), "cubic", False)(
+            xq[:m].cpu().numpy(), yq[:m].cpu().numpy(), *d)
+        res.append({"config": f"C3 bicubic 2048^2, 2.5e8 queries, derivative={d}, extrap=False, f64",
+                    "queries_per_s_random": nq / ms_r * 1e3, "queries_per_s_sorted": nq / ms_s * 1e3,
+                    "roofline_frac_random": bytes_ / (ms_r * 1e-3) / 1e9 / PEAK,
+                    "roofline_frac_sorted": bytes_ / (ms_s * 1e-3) / 1e9 / PEAK,
+                    "parity": parity(got, want, 1e-12)})
+    return res
+
+
+def c5():
+    res = []
+    n = 512
+    nq = 125_000_000  # one GPU's share of 1e9 over 8 GPUs
+    for tdt, name, rtol in ((torch.float64, "f64", 1e-12), (torch.float32, "f32", 1e-5)):
+        g = torch.Generator(device=dev).manual_seed(1239)
+        x = torch.linspace(0, 1, n, dtype=tdt, device=dev)
+        f = torch.randn((n, n, n), dtype=tdt, device=dev, generator=g)
+        ip = ipx.Interpolator3D(x, x, x, f, "cubic")
+        q = [torch.rand(nq, dtype=tdt, device=dev, generator=g) for _ in range(3)]
+        key = ((q[0] * (n - 1)).floor().long() * n + (q[1] * (n - 1)).floor().long()) * n + (q[2] * (n - 1)).floor().long()
+        o = torch.argsort(key)
+        del key
+        s = [a[o] for a in q]
+        del o
+        obuf = torch.empty(nq, dtype=tdt, device=dev)
+        elem = 8 if name == "f64" else 4
+        bytes_ = nq * 4 * elem + 8 * n**3 * elem
+        # jit(vmap(grad(interp, argnums=0))) == one derivative-(1,0,0) evaluation
+        ms_r = timed(lambda: ip(*q, 1, 0, 0, out=obuf), 3, 2)
+        ms_s = timed(lambda: ip(*s, 1, 0, 0, out=obuf), 3, 2)
+        m = 1 << 11
+        got = ip(*[a[:m] for a in s], 1, 0, 0).cpu().numpy()
+        xs = x.cpu().numpy()
+        fx = {k: v.cpu().numpy() for k, v in ip.derivs.items()}  # slopes verified separately by the tests
+        want = O.interp3d(*[a[:m].cpu().numpy() for a in s], xs, xs, xs, f.cpu().numpy(), "cubic", (1, 0, 0), **fx)
+        res.append({"config": f"C5 Interpolator3D 512^3 d/dxq, 1.25e8 queries (1 GPU share), {name}",
+                    "queries_per_s_random": nq / ms_r * 1e3, "queries_per_s_sorted": nq / ms_s * 1e3,
+                    "roofline_frac_random": bytes_ / (ms_r * 1e-3) / 1e9 / PEAK,
+                    "roofline_frac_sorted": bytes_ / (ms_s * 1e-3) / 1e9 / PEAK,
+                    "parity": parity(got, want, rtol)})
+        del ip, f, q, s, obuf
+        torch.cuda.empty_cache()
+    return res
+
+
+if __name__ == "__main__":
+    which = [a.lower() for a in sys.argv[1:]] or ["c1", "c2", "c3", "c5"]
+    for name in which:
+        r = {"c1": c1, "c2": c2, "c3": c3, "c5": c5}[name]()
+        for item in (r if isinstance(r, list) else [r]):
+            print(json.dumps(item), flush=True)
