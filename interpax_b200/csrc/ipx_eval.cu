@@ -16,6 +16,7 @@
 // (64 + 16 + 4 FMAs in 3-D instead of 4096 + 64).
 #include <cuda_runtime.h>
 
+#include "ipx_contract.cuh"
 #include "ipx_device.cuh"
 
 #define IPX_STR2(x) #x
@@ -80,56 +81,23 @@ __device__ __forceinline__ T apply_extrap(const EvalArgs<T, ND>& a, const ipx_pa
 }
 
 // ------------------------------------------------------------------------------------
-// cubic family
+// cubic family: weights once per query, then per batch element two node layers
 // ------------------------------------------------------------------------------------
 template <typename T, int ND, int LAYOUT>
-__device__ __forceinline__ T eval_cubic(const EvalArgs<T, ND>& a, const ipx_params& P,
-                                        const AxisLoc<T>* L, int64_t b) {
-  T w[ND][4];
-#pragma unroll
-  for (int ax = 0; ax < ND; ++ax) hermite_weights(L[ax], P.axis[ax].derivative, w[ax]);
-
+__device__ __forceinline__ T eval_cubic(const EvalArgs<T, ND>& a, const AxisLoc<T>* L,
+                                        const T (*w)[4], int64_t b) {
+  WeightRefs<T, ND, 1> W;
+  W.w[0] = w;
   T res = T(0);
-  if (ND == 1) {
 #pragma unroll
-    for (int ii = 0; ii < 2; ++ii) {
-      T r[2];
-      load_record<T, ND, LAYOUT>(a, node_index<T, ND>(a, L, ii) * a.batch + b, r);
-      res += r[0] * w[0][ii] + r[1] * w[0][2 + ii];
-    }
-  } else if (ND == 2) {
-#pragma unroll
-    for (int ii = 0; ii < 2; ++ii) {
-      T p[2] = {T(0), T(0)};
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        T r[4];
-        load_record<T, ND, LAYOUT>(a, node_index<T, ND>(a, L, ii | (jj << 1)) * a.batch + b, r);
-        p[0] += r[0] * w[1][jj] + r[1] * w[1][2 + jj];
-        p[1] += r[2] * w[1][jj] + r[3] * w[1][2 + jj];
-      }
-      res += p[0] * w[0][ii] + p[1] * w[0][2 + ii];
-    }
-  } else {
-#pragma unroll
-    for (int ii = 0; ii < 2; ++ii) {
-      T v[2] = {T(0), T(0)};
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        T p[4] = {T(0), T(0), T(0), T(0)};
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-          T r[8];
-          load_record<T, ND, LAYOUT>(
-              a, node_index<T, ND>(a, L, ii | (jj << 1) | (kk << 2)) * a.batch + b, r);
-#pragma unroll
-          for (int m = 0; m < 4; ++m) p[m] += r[2 * m] * w[2][kk] + r[2 * m + 1] * w[2][2 + kk];
-        }
-        v[0] += p[0] * w[1][jj] + p[1] * w[1][2 + jj];
-        v[1] += p[2] * w[1][jj] + p[3] * w[1][2 + jj];
-      }
-      res += v[0] * w[0][ii] + v[1] * w[0][2 + ii];
-    }
+  for (int kk = 0; kk < 2; ++kk) {
+    T A[1][2];
+    layer_contract<T, ND, 1>(
+        [&](int c, T* r) {
+          load_record<T, ND, LAYOUT>(a, node_index<T, ND>(a, L, c | (kk << (ND - 1))) * a.batch + b, r);
+        },
+        W, A);
+    res = fma(A[0][0], w[ND - 1][kk], fma(A[0][1], w[ND - 1][2 + kk], res));
   }
   return res;
 }
@@ -137,9 +105,25 @@ __device__ __forceinline__ T eval_cubic(const EvalArgs<T, ND>& a, const ipx_para
 // ------------------------------------------------------------------------------------
 // linear
 // ------------------------------------------------------------------------------------
+template <typename T, int ND> struct LinearW {
+  T w[ND][2];
+  T scale;
+};
+
+template <typename T, int ND>
+__device__ __forceinline__ void linear_setup(const ipx_params& P, const AxisLoc<T>* L, LinearW<T, ND>& W) {
+  W.scale = T(1);
+#pragma unroll
+  for (int ax = 0; ax < ND; ++ax) {
+    T dxi;
+    linear_weights(L[ax], P.axis[ax].derivative, W.w[ax], dxi);
+    W.scale = ax == 0 ? dxi : W.scale * dxi;
+  }
+}
+
 template <typename T, int ND>
 __device__ __forceinline__ T eval_linear(const EvalArgs<T, ND>& a, const ipx_params& P,
-                                         const AxisLoc<T>* L, int64_t b) {
+                                         const AxisLoc<T>* L, const LinearW<T, ND>& W, int64_t b) {
   const T* __restrict__ f = a.tab[0];
   if (ND == 1) {
     // _spline.py:542-567
@@ -155,36 +139,28 @@ __device__ __forceinline__ T eval_linear(const EvalArgs<T, ND>& a, const ipx_par
     return dx == T(0) ? f1 : f0 + (delta * dxi) * df;
   }
   // _spline.py:728-755, 982-1023:  dxi*dyi[*dzi] * sum F * tx * ty [* tz]
-  T w[ND][2];
-  T scale = T(1);
-#pragma unroll
-  for (int ax = 0; ax < ND; ++ax) {
-    T dxi;
-    linear_weights(L[ax], P.axis[ax].derivative, w[ax], dxi);
-    scale = ax == 0 ? dxi : scale * dxi;
-  }
   T s = T(0);
 #pragma unroll
   for (int c = 0; c < (1 << ND); ++c) {
     T val = ldg(f + node_index<T, ND>(a, L, c) * a.batch + b);
-    T wt = w[0][c & 1];
+    T wt = W.w[0][c & 1];
 #pragma unroll
-    for (int ax = 1; ax < ND; ++ax) wt *= w[ax][(c >> ax) & 1];
+    for (int ax = 1; ax < ND; ++ax) wt *= W.w[ax][(c >> ax) & 1];
     s += val * wt;
   }
-  return scale * s;
+  return W.scale * s;
 }
 
 // ------------------------------------------------------------------------------------
-// nearest
+// nearest: returns the node index (times batch not applied) of the selected knot/corner,
+// or -1 when the result is identically zero (derivative requested)
 // ------------------------------------------------------------------------------------
 template <typename T, int ND>
-__device__ __forceinline__ T eval_nearest(const EvalArgs<T, ND>& a, const ipx_params& P,
-                                          const AxisLoc<T>* L, int64_t b) {
-  const T* __restrict__ f = a.tab[0];
+__device__ __forceinline__ int64_t nearest_node(const EvalArgs<T, ND>& a, const ipx_params& P,
+                                                const AxisLoc<T>* L) {
   if (ND == 1) {
     // _spline.py:531-538: argmin_k |q - x[k]| over ALL knots, first minimum wins.
-    if (P.axis[0].derivative >= 1) return T(0);
+    if (P.axis[0].derivative >= 1) return -1;
     const AxisDesc<T>& A = a.ax[0];
     T q = L[0].q;
     int c;
@@ -206,14 +182,14 @@ __device__ __forceinline__ T eval_nearest(const EvalArgs<T, ND>& a, const ipx_pa
         c = lo;
       }
     }
-    return ldg(f + (int64_t)padded_to_table(A, c) * a.batch + b);
+    return padded_to_table(A, c);
   }
   // _spline.py:704-726, 942-980: nearest (Euclidean) of the cell corners; the corner
   // order puts the UPPER knot first on every axis, x fastest; first minimum wins.
   bool all_zero = true;
 #pragma unroll
   for (int ax = 0; ax < ND; ++ax) all_zero = all_zero && (P.axis[ax].derivative == 0);
-  if (!all_zero) return T(0);
+  if (!all_zero) return -1;
   T best = T(0);
   int best_c = 0;
 #pragma unroll
@@ -231,14 +207,25 @@ __device__ __forceinline__ T eval_nearest(const EvalArgs<T, ND>& a, const ipx_pa
     if (take) { best = dist; best_c = c; }
   }
   // corner bit set = LOWER knot here; node_index wants bit set = upper
-  return ldg(f + node_index<T, ND>(a, L, (~best_c) & ((1 << ND) - 1)) * a.batch + b);
+  return node_index<T, ND>(a, L, (~best_c) & ((1 << ND) - 1));
 }
 
 // ------------------------------------------------------------------------------------
-// the kernel
+// the generic kernel.  Lane mapping: a query owns 2^bpad_log2 adjacent lanes which stride over
+// the batch (trailing dims of f), so the search and the weights are computed once per lane and
+// reused for its batch elements, table reads are contiguous in the batch index and the
+// (nq, batch) result is written coalesced.  batch == 1 degenerates to one lane per query.
 // ------------------------------------------------------------------------------------
+// Queries a lane handles per round.  Batched evaluation is a dependent chain per query
+// (search -> gather -> store) with little arithmetic, so several independent queries are
+// kept in flight per lane to cover the memory latency; in 3-D the register cost is too high.
+template <int ND> struct QueriesPerRound {
+  static constexpr int value = ND == 1 ? 4 : (ND == 2 ? 2 : 1);
+};
+
 template <typename T, int ND, int METHOD, int LAYOUT>
-__global__ void __launch_bounds__(kThreads) eval_kernel(const EvalArgs<T, ND> a) {
+__global__ void __launch_bounds__(kThreads) eval_kernel(const EvalArgs<T, ND> a, int bpad_log2) {
+  constexpr int U = QueriesPerRound<ND>::value;
   __shared__ AxisConst<T> consts[ND];
   __shared__ ipx_params params_s;
   if (threadIdx.x < ND) axis_consts(a.ax[threadIdx.x], consts[threadIdx.x]);
@@ -246,25 +233,74 @@ __global__ void __launch_bounds__(kThreads) eval_kernel(const EvalArgs<T, ND> a)
   __syncthreads();
   const ipx_params& P = params_s;
 
-  const int64_t total = a.nq * a.batch;
-  const int64_t stride = (int64_t)gridDim.x * kThreads;
-  for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < total; e += stride) {
-    int64_t qi, b;
-    if (a.batch == 1) { qi = e; b = 0; } else { qi = e / a.batch; b = e - qi * a.batch; }
+  const int lane = threadIdx.x & 31;
+  const int bpad = 1 << bpad_log2;
+  const int qpw = 32 >> bpad_log2;  // queries per warp per sub-round
+  const int qsub = lane >> bpad_log2;
+  const int b0 = lane & (bpad - 1);
+  const int64_t warps = (int64_t)gridDim.x * (kThreads / 32);
+  const int64_t wg = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (b0 >= a.batch) return;  // padding lanes (no warp-level sync below)
 
-    AxisLoc<T> L[ND];
+  for (int64_t qbase = wg * qpw * U; qbase < a.nq; qbase += warps * qpw * U) {
+    AxisLoc<T> L[U][ND];
+    bool valid[U];
 #pragma unroll
-    for (int ax = 0; ax < ND; ++ax) locate(a.ax[ax], consts[ax], P.axis[ax], qi, L[ax]);
-
-    T v;
-    if (METHOD == IPX_CUBIC) v = eval_cubic<T, ND, LAYOUT>(a, P, L, b);
-    else if (METHOD == IPX_LINEAR) v = eval_linear<T, ND>(a, P, L, b);
-    else v = eval_nearest<T, ND>(a, P, L, b);
-
-    a.out[e] = apply_extrap<T, ND>(a, P, L, v);
-    if (a.idx_out != nullptr && b == 0) {
+    for (int u = 0; u < U; ++u) {
+      const int64_t qi = qbase + u * qpw + qsub;
+      valid[u] = qi < a.nq;
+      const int64_t qs = valid[u] ? qi : 0;  // harmless in-range index for the idle slots
 #pragma unroll
-      for (int ax = 0; ax < ND; ++ax) a.idx_out[(int64_t)ax * a.nq + qi] = L[ax].i;
+      for (int ax = 0; ax < ND; ++ax) locate(a.ax[ax], consts[ax], P.axis[ax], qs, L[u][ax]);
+    }
+
+    if (METHOD == IPX_CUBIC) {
+      T w[U][ND][4];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int ax = 0; ax < ND; ++ax) hermite_weights(L[u][ax], P.axis[ax].derivative, w[u][ax]);
+      for (int64_t b = b0; b < a.batch; b += bpad) {
+        T v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = eval_cubic<T, ND, LAYOUT>(a, L[u], w[u], b);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (valid[u]) a.out[(qbase + u * qpw + qsub) * a.batch + b] = apply_extrap<T, ND>(a, P, L[u], v[u]);
+      }
+    } else if (METHOD == IPX_LINEAR) {
+      LinearW<T, ND> W[U];
+      if (ND > 1) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) linear_setup<T, ND>(P, L[u], W[u]);
+      }
+      for (int64_t b = b0; b < a.batch; b += bpad) {
+        T v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = eval_linear<T, ND>(a, P, L[u], W[u], b);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (valid[u]) a.out[(qbase + u * qpw + qsub) * a.batch + b] = apply_extrap<T, ND>(a, P, L[u], v[u]);
+      }
+    } else {
+      int64_t node[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) node[u] = nearest_node<T, ND>(a, P, L[u]);
+      for (int64_t b = b0; b < a.batch; b += bpad) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          T v = node[u] < 0 ? T(0) : ldg(a.tab[0] + node[u] * a.batch + b);
+          if (valid[u]) a.out[(qbase + u * qpw + qsub) * a.batch + b] = apply_extrap<T, ND>(a, P, L[u], v);
+        }
+      }
+    }
+    if (a.idx_out != nullptr && b0 == 0) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!valid[u]) continue;
+#pragma unroll
+        for (int ax = 0; ax < ND; ++ax) a.idx_out[(int64_t)ax * a.nq + qbase + u * qpw + qsub] = L[u][ax].i;
+      }
     }
   }
 }
@@ -364,17 +400,19 @@ static int launch_eval(const T* const* q, int64_t nq, const T* const* knots,
   }
 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  int grid = grid_for(nq * batch, kThreads);
+  int bpad_log2 = 0;  // lanes per query = smallest power of two >= min(batch, 32)
+  while ((1 << bpad_log2) < 32 && (int64_t)(1 << bpad_log2) < batch) ++bpad_log2;
+  int grid = grid_for(((nq << bpad_log2) + QueriesPerRound<ND>::value - 1) / QueriesPerRound<ND>::value, kThreads);
   if (method == IPX_CUBIC) {
     if (layout == IPX_AOS) {
       // scalar-valued packed tables: the warp-cooperative shared-memory kernel
       const bool tiled = batch == 1 && launch_tile<T, ND>(a, s);
-      if (!tiled) eval_kernel<T, ND, IPX_CUBIC, IPX_AOS><<<grid, kThreads, 0, s>>>(a);
-    } else eval_kernel<T, ND, IPX_CUBIC, IPX_SOA><<<grid, kThreads, 0, s>>>(a);
+      if (!tiled) eval_kernel<T, ND, IPX_CUBIC, IPX_AOS><<<grid, kThreads, 0, s>>>(a, bpad_log2);
+    } else eval_kernel<T, ND, IPX_CUBIC, IPX_SOA><<<grid, kThreads, 0, s>>>(a, bpad_log2);
   } else if (method == IPX_LINEAR) {
-    eval_kernel<T, ND, IPX_LINEAR, IPX_SOA><<<grid, kThreads, 0, s>>>(a);
+    eval_kernel<T, ND, IPX_LINEAR, IPX_SOA><<<grid, kThreads, 0, s>>>(a, bpad_log2);
   } else {
-    eval_kernel<T, ND, IPX_NEAREST, IPX_SOA><<<grid, kThreads, 0, s>>>(a);
+    eval_kernel<T, ND, IPX_NEAREST, IPX_SOA><<<grid, kThreads, 0, s>>>(a, bpad_log2);
   }
   return cudaPeekAtLastError() == cudaSuccess ? IPX_OK : IPX_ELAUNCH;
 }
