@@ -47,13 +47,22 @@ template <typename T, int ND> struct TileCfg {
   static constexpr int WARP_TILE_BYTES = NC * kRunCap * STRIDE;
 };
 
-// cubic Hermite weights from the local coordinate pieces (same formulas as hermite_weights)
+// rare paths kept out of line (values in and out through registers only): the hot loop must
+// stay small for the instruction caches
+template <typename T> __device__ __noinline__ T py_mod_slow(T q, T P) { return py_mod(q, P); }
 template <typename T>
+__device__ __noinline__ int bin_index_slow(const T* x, int n, T q, T x_first, T inv_h) {
+  T lo, hi;
+  return bin_index(x, n, q, x_first, inv_h, lo, hi);
+}
+
+// cubic Hermite weights from the local coordinate pieces (same formulas as hermite_weights)
+template <typename T, bool ORD0>
 __device__ __forceinline__ void hermite_weights_r(T q, T x0, T x1, int order, T dxi, T w[4]) {
   T dx = x1 - x0;
   T t = (q - x0) * dxi;
   T tt0, tt1, tt2, tt3;
-  if (order <= 0) {
+  if (ORD0 || order <= 0) {
     tt0 = T(1); tt1 = t; tt2 = t * t; tt3 = tt2 * t;
   } else if (order == 1) {
     tt0 = T(0); tt1 = dxi; tt2 = (T(2) * t) * dxi; tt3 = (T(3) * (t * t)) * dxi;
@@ -99,7 +108,9 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.wait_all;\n" ::: "memory");
 }
 
-template <typename T, int ND, bool DEVP>
+// DEVP: traced operands are read from device memory.  ORD0: every derivative order is 0 (known
+// on the host when the operands are host-resident), which drops the order switch from the loop.
+template <typename T, int ND, bool DEVP, bool ORD0>
 __global__ void __launch_bounds__(kTileThreads, 2)
 eval_tile_kernel(const EvalArgs<T, ND> a) {
   using Cfg = TileCfg<T, ND>;
@@ -164,7 +175,7 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
         T r = q;
         r = q < T(0) ? q + Pd : r;      // [-P,0): fmod leaves q, the sign fix adds P
         r = q >= Pd ? q - Pd : r;       // [P,2P]: exact (Sterbenz)
-        if (!(q >= -Pd && q <= Pd + Pd)) r = py_mod(q, Pd);  // anything else: the exact remainder
+        if (!(q >= -Pd && q <= Pd + Pd)) r = py_mod_slow(q, Pd);  // anything else: exact remainder
         q = r;
       }
       const int nk = A.nk;
@@ -177,10 +188,12 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
       T lo = ks[i - 1], hi = ks[i];
       // exact check of the guess against the knots (NaN fails it); the rare miss re-searches
       if (!((q >= lo || i == 1) && (q < hi || i == nk - 1))) {
-        i = bin_index(ks, nk, q, xf, ih, lo, hi);
+        i = bin_index_slow(ks, nk, q, xf, ih);
+        lo = ks[i - 1];
+        hi = ks[i];
       }
       S.li[ax] = i;
-      hermite_weights_r(q, lo, hi, P.axis[ax].derivative, ks[nk + i], S.w[ax]);
+      hermite_weights_r<T, ORD0>(q, lo, hi, P.axis[ax].derivative, ks[nk + i], S.w[ax]);
       if (!A.wrap) {
         const ipx_axis_params& pa = P.axis[ax];
         if (!pa.keep_lo && q < xf) S.fill |= 1u << (2 * ax);
@@ -437,7 +450,10 @@ static bool launch_tile(const EvalArgs<T, ND>& a, cudaStream_t s) {
     if (total_knots > kSmemKnotCap) return false;
     if ((reinterpret_cast<uintptr_t>(a.tab[0]) & 15) != 0) return false;
     const size_t smem = tile_smem_bytes<T, ND>(a);
-    auto kern = a.dp ? eval_tile_kernel<T, ND, true> : eval_tile_kernel<T, ND, false>;
+    bool ord0 = a.dp == nullptr;
+    for (int ax = 0; ax < ND && ord0; ++ax) ord0 = a.hp.axis[ax].derivative <= 0;
+    auto kern = a.dp ? eval_tile_kernel<T, ND, true, false>
+                     : (ord0 ? eval_tile_kernel<T, ND, false, true> : eval_tile_kernel<T, ND, false, false>);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return false;
     int dev = 0, sms = 148, per_sm = 1;
