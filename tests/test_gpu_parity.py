@@ -595,3 +595,40 @@ def test_full_size_properties_c3():
     xs, ys = xq[:m].cpu().numpy(), yq[:m].cpu().numpy()
     assert_parity(r0[:m].cpu().numpy(), o(xs, ys))
     assert_parity(r1[:m].cpu().numpy(), o(xs, ys, 1, 0))
+
+
+# ------------------------------------------------------------------ host-resident queries
+def test_host_streaming_matches_device_path():
+    """NumPy / CPU-tensor queries are streamed through the GPU in chunks over several CUDA
+    streams; the result must be bit-identical to the all-on-device call, for pageable and
+    pinned buffers, with and without a caller-provided `out`."""
+    from interpax_b200 import api
+
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(77)
+    n = 48
+    x = torch.linspace(0, 1, n, dtype=torch.float64, device=dev)
+    f = torch.randn((n, n, n), dtype=torch.float64, device=dev, generator=g)
+    ip = ipx.Interpolator3D(x, x, x, f, "cubic", True)
+    nq = 2 * api._HOST_CHUNK + 12345  # three chunks, odd tail
+    qd = [torch.rand(nq, dtype=torch.float64, device=dev, generator=g) * 1.1 - 0.05 for _ in range(3)]
+    want = ip(*qd)
+    assert want.is_cuda
+    qh = [q.cpu() for q in qd]
+    got = ip(*qh)                                   # pageable CPU tensors -> CPU tensor
+    assert isinstance(got, torch.Tensor) and not got.is_cuda
+    assert torch.equal(got, want.cpu())
+    qp = [q.pin_memory() for q in qh]
+    out = torch.empty(nq, dtype=torch.float64, pin_memory=True)
+    ret = ip(*qp, out=out)                          # pinned in, pinned out
+    assert ret.data_ptr() == out.data_ptr() and torch.equal(out, want.cpu())
+    got_np = ip(*[q.numpy() for q in qh])           # NumPy in -> NumPy out
+    assert isinstance(got_np, np.ndarray) and np.array_equal(got_np, want.cpu().numpy())
+    assert api.launches_per_host_call(nq) == 3
+    # batch > 1 through the same path
+    fb = torch.randn((n, n, 3), dtype=torch.float64, device=dev, generator=g)
+    ip2 = ipx.Interpolator2D(x, x, fb, "cubic", True)
+    m = api._HOST_CHUNK + 7
+    assert torch.equal(ip2(qh[0][:m], qh[1][:m]), ip2(qd[0][:m], qd[1][:m]).cpu())
+    with pytest.raises(ValueError):
+        ip(*qd, out=out)                            # device queries need a device `out`
