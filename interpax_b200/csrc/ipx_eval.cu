@@ -308,6 +308,7 @@ __global__ void __launch_bounds__(kThreads) eval_kernel(const EvalArgs<T, ND> a,
 }  // namespace ipx
 
 #include "ipx_eval_tile.cuh"
+#include "ipx_eval_rows.cuh"
 
 namespace ipx {
 
@@ -403,6 +404,11 @@ static int launch_eval(const T* const* q, int64_t nq, const T* const* knots,
   int bpad_log2 = 0;  // lanes per query = smallest power of two >= min(batch, 32)
   while ((1 << bpad_log2) < 32 && (int64_t)(1 << bpad_log2) < batch) ++bpad_log2;
   int grid = grid_for(((nq << bpad_log2) + QueriesPerRound<ND>::value - 1) / QueriesPerRound<ND>::value, kThreads);
+  if constexpr (ND == 1) {
+    // wide vector-valued 1-D tables: the row-streaming kernel
+    if (launch_rows<T>(a, method, layout, s))
+      return cudaPeekAtLastError() == cudaSuccess ? IPX_OK : IPX_ELAUNCH;
+  }
   if (method == IPX_CUBIC) {
     if (layout == IPX_AOS) {
       // scalar-valued packed tables: the warp-cooperative shared-memory kernel

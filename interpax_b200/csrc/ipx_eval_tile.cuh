@@ -33,18 +33,18 @@ namespace ipx {
 
 constexpr int kTileThreads = 256;
 constexpr int kTileWarps = kTileThreads / 32;
-constexpr int kRunCap = 16;         // nodes of one run held per column
 constexpr int kMaxGroups = 4;       // more distinct columns than this in a warp -> direct path
 constexpr int kSmemKnotCap = 3072;  // total knots (all axes) staged in shared memory
 
-template <typename T, int ND> struct TileCfg {
+// RC = nodes of one run held per column (16: dense queries, several per cell; 32: sparse ones)
+template <typename T, int ND, int RC = 16> struct TileCfg {
   static constexpr int NT = 1 << ND;                       // values per record
   static constexpr int NC = 1 << (ND - 1);                 // columns per group
   static constexpr int NCA = ND > 1 ? ND - 1 : 1;          // column axes (array extent)
   static constexpr int REC_BYTES = NT * (int)sizeof(T);
   static constexpr int CH = REC_BYTES / 16;                // 16-byte chunks per record
   static constexpr int STRIDE = REC_BYTES + (REC_BYTES >= 32 ? 16 : 0);  // bank-conflict padding
-  static constexpr int WARP_TILE_BYTES = NC * kRunCap * STRIDE;
+  static constexpr int WARP_TILE_BYTES = NC * RC * STRIDE;
 };
 
 // rare paths kept out of line (values in and out through registers only): the hot loop must
@@ -110,10 +110,11 @@ __device__ __forceinline__ void cp_async_wait_all() {
 
 // DEVP: traced operands are read from device memory.  ORD0: every derivative order is 0 (known
 // on the host when the operands are host-resident), which drops the order switch from the loop.
-template <typename T, int ND, bool DEVP, bool ORD0>
+template <typename T, int ND, bool DEVP, bool ORD0, int RC>
 __global__ void __launch_bounds__(kTileThreads, 2)
 eval_tile_kernel(const EvalArgs<T, ND> a) {
-  using Cfg = TileCfg<T, ND>;
+  using Cfg = TileCfg<T, ND, RC>;
+  constexpr int kRunCap = RC;
   constexpr int LPC = 32 / Cfg::NC;          // lanes that copy one column
   constexpr int NPR = LPC / Cfg::CH;         // nodes of a column copied per round
   static_assert(LPC % Cfg::CH == 0 && NPR >= 1, "column copy layout");
@@ -423,11 +424,32 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
 }
 
 // dynamic shared memory the tile kernel needs
-template <typename T, int ND> static size_t tile_smem_bytes(const EvalArgs<T, ND>& a) {
+template <typename T, int ND, int RC> static size_t tile_smem_bytes(const EvalArgs<T, ND>& a) {
   size_t knots = 0;
   for (int ax = 0; ax < ND; ++ax) knots += 2 * (size_t)a.ax[ax].nk * sizeof(T);
   knots = (knots + 15) & ~(size_t)15;
-  return knots + (size_t)kTileWarps * TileCfg<T, ND>::WARP_TILE_BYTES;
+  return knots + (size_t)kTileWarps * TileCfg<T, ND, RC>::WARP_TILE_BYTES;
+}
+
+template <typename T, int ND, int RC>
+static bool launch_tile_rc(const EvalArgs<T, ND>& a, cudaStream_t s) {
+  const size_t smem = tile_smem_bytes<T, ND, RC>(a);
+  bool ord0 = a.dp == nullptr;
+  for (int ax = 0; ax < ND && ord0; ++ax) ord0 = a.hp.axis[ax].derivative <= 0;
+  auto kern = a.dp ? eval_tile_kernel<T, ND, true, false, RC>
+                   : (ord0 ? eval_tile_kernel<T, ND, false, true, RC> : eval_tile_kernel<T, ND, false, false, RC>);
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return false;
+  int dev = 0, sms = 148, per_sm = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, smem);
+  if (per_sm < 1) per_sm = 1;
+  int64_t need = (a.nq + 2 * kTileThreads - 1) / (2 * kTileThreads);
+  int64_t grid = (int64_t)sms * per_sm;  // persistent: one resident wave
+  if (need < grid) grid = need;
+  kern<<<(int)grid, kTileThreads, smem, s>>>(a);
+  return true;
 }
 
 // true if (T, ND) has a tile kernel: records of at least 16 bytes
@@ -449,23 +471,12 @@ static bool launch_tile(const EvalArgs<T, ND>& a, cudaStream_t s) {
     }
     if (total_knots > kSmemKnotCap) return false;
     if ((reinterpret_cast<uintptr_t>(a.tab[0]) & 15) != 0) return false;
-    const size_t smem = tile_smem_bytes<T, ND>(a);
-    bool ord0 = a.dp == nullptr;
-    for (int ax = 0; ax < ND && ord0; ++ax) ord0 = a.hp.axis[ax].derivative <= 0;
-    auto kern = a.dp ? eval_tile_kernel<T, ND, true, false>
-                     : (ord0 ? eval_tile_kernel<T, ND, false, true> : eval_tile_kernel<T, ND, false, false>);
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return false;
-    int dev = 0, sms = 148, per_sm = 1;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, smem);
-    if (per_sm < 1) per_sm = 1;
-    int64_t need = (a.nq + 2 * kTileThreads - 1) / (2 * kTileThreads);
-    int64_t grid = (int64_t)sms * per_sm;  // persistent: one resident wave
-    if (need < grid) grid = need;
-    kern<<<(int)grid, kTileThreads, smem, s>>>(a);
-    return true;
+    // queries per cell decides how long a run the tile must hold: few queries per cell means
+    // a warp's 64 consecutive (sorted) queries span many cells along the last axis
+    double cells = 1.0;
+    for (int ax = 0; ax < ND; ++ax) cells *= (double)(a.ax[ax].n > 1 ? a.ax[ax].n - 1 : 1);
+    const bool sparse = (double)a.nq < 2.0 * cells;
+    return sparse ? launch_tile_rc<T, ND, 32>(a, s) : launch_tile_rc<T, ND, 16>(a, s);
   }
 }
 

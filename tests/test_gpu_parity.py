@@ -622,7 +622,9 @@ def test_host_streaming_matches_device_path():
     out = torch.empty(nq, dtype=torch.float64, pin_memory=True)
     ret = ip(*qp, out=out)                          # pinned in, pinned out
     assert ret.data_ptr() == out.data_ptr() and torch.equal(out, want.cpu())
-    got_np = ip(*[q.numpy() for q in qh])           # NumPy in -> NumPy out
+    xn = x.cpu().numpy()                            # NumPy everywhere -> NumPy out
+    ipn = ipx.Interpolator3D(xn, xn, xn, f.cpu().numpy(), "cubic", True)
+    got_np = ipn(*[q.numpy() for q in qh])
     assert isinstance(got_np, np.ndarray) and np.array_equal(got_np, want.cpu().numpy())
     assert api.launches_per_host_call(nq) == 3
     # batch > 1 through the same path
@@ -632,3 +634,44 @@ def test_host_streaming_matches_device_path():
     assert torch.equal(ip2(qh[0][:m], qh[1][:m]), ip2(qd[0][:m], qd[1][:m]).cpu())
     with pytest.raises(ValueError):
         ip(*qd, out=out)                            # device queries need a device `out`
+
+
+# ------------------------------------------------------------------ wide vector-valued 1-D tables (C2 shape)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("B", [32, 64, 70, 130])
+def test_wide_batch_1d_rows_kernel(B, dtype):
+    """f of shape (Nx, B) with B >= 32 takes the row-streaming kernel (lanes = columns, rows
+    reused while the interval does not change): functional (SoA) and class (AoS) forms, linear
+    and cubic, sorted / random / clustered queries, extrapolation fills, periodic wrap,
+    derivatives, a query count that is not a multiple of the warp size."""
+    rng = np.random.default_rng(B)
+    n = 57
+    x = knots_nonuniform(rng, n, -1.0, 2.0, dtype)
+    f = rng.normal(size=(n, B)).astype(dtype)
+    nq = 1000 + 13
+    q_rand = rng.uniform(-1.3, 2.3, nq).astype(dtype)
+    q_sort = np.sort(q_rand)
+    q_clus = np.repeat(rng.uniform(-1, 2, 40), 26)[:nq].astype(dtype)
+    q_clus[5] = np.nan
+    up = lambda v: v.astype(np.float64) if dtype == np.float32 else None
+    for q in (q_rand, q_sort, q_clus):
+        for method, deriv, extrap, period in [
+            ("cubic", 0, False, None), ("cubic", 1, (True, 0.5), None), ("linear", 0, (2.0, False), None),
+            ("linear", 1, True, None), ("monotonic", 2, True, None), ("cubic", 0, False, 3.3),
+            ("akima", 0, True, None), ("cubic2", 3, False, None),
+        ]:
+            what = f"B={B} {method} d={deriv} ex={extrap} per={period}"
+            want = O.interp1d(q, x, f, method, deriv, extrap, period)
+            got = ipx.interp1d(q, x, f, method, deriv, extrap, period)
+            truth = None
+            if dtype == np.float32:
+                truth = O.interp1d(up(q), up(x), up(f), method, deriv, extrap, period)
+            assert_parity(got, want, "fn " + what, truth)
+            want_c = O.Interpolator1D(x, f, method, extrap, period)(q, deriv)
+            got_c = ipx.Interpolator1D(x, f, method, extrap, period)(q, deriv)
+            truth_c = None
+            if dtype == np.float32:
+                truth_c = O.Interpolator1D(up(x), up(f), method, extrap, period)(up(q), deriv)
+            assert_parity(got_c, want_c, "cls " + what, truth_c)
+    res, idx = api._interp(1, (q_rand,), (x,), f, "cubic", 0, True, None, {}, return_index=True)
+    assert np.array_equal(idx[0], O.bin_index(x, q_rand))
