@@ -330,6 +330,88 @@ __global__ void cubic2_solve_kernel(const SlopeArgs<T> a, const BcArgs<T> bc,
   }
 }
 
+// ---- long axes: windowed Thomas ------------------------------------------------------
+// The spline system is strictly diagonally dominant in its interior rows
+// (|lower| + |upper| = diag / 2 for any knot spacing), so the influence of a row on the
+// solution decays at least like (2 - sqrt(3))^distance = 0.268^distance.  A chunk of rows can
+// therefore be solved from a window that extends kHalo = 64 rows beyond it (0.268^64 = 2e-37:
+// far below one ulp) instead of from the whole axis: forward elimination enters the chunk
+// through the left halo, a backward elimination through the right halo supplies the value
+// just past the chunk, and back substitution covers the chunk.  Chunks at the ends of the
+// axis include the true boundary rows.  This turns the 2 n sequential steps per column of the
+// plain Thomas sweep into n / kChunk independent pieces per column (1e6 knots x 64 columns:
+// 1.4 s -> milliseconds) with results equal to the sequential sweep up to rounding.
+constexpr int kChunk = 256;
+constexpr int kHalo = 64;
+
+// matrix-only part for every chunk: c'_k of the chunk's own rows -> ws[k]
+template <typename T>
+__global__ void cubic2_wfactor_kernel(const T* __restrict__ x, int n, int bs, int be,
+                                      T* __restrict__ ws) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = p * kChunk;
+  if (s >= n) return;
+  const int e = min(n, s + kChunk);
+  T cprev = T(0);
+  for (int k = max(0, s - kHalo); k < e; ++k) {
+    T lo, di, up;
+    bool masked;
+    cubic2_row(x, n, bs, be, k, lo, di, up, masked);
+    const T den = di - lo * cprev;
+    cprev = up / den;
+    if (k >= s) ws[k] = cprev;
+  }
+}
+
+template <typename T>
+__global__ void cubic2_wsolve_kernel(const SlopeArgs<T> a, const BcArgs<T> bc,
+                                     const T* __restrict__ ws) {
+  const int64_t cols = a.outer * a.inner;
+  const int n = a.n;
+  const int chunks = (n + kChunk - 1) / kChunk;
+  const int64_t total = cols * chunks;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int64_t col = t % cols;
+    const int p = (int)(t / cols);
+    const int64_t o = col / a.inner, i = col - o * a.inner;
+    const int64_t base = o * n * a.inner + i;
+    const int s = p * kChunk, e = min(n, s + kChunk);
+    // forward elimination: left halo (nothing stored), then the chunk (d' -> out)
+    T cprev = T(0), dprev = T(0);
+    for (int k = max(0, s - kHalo); k < e; ++k) {
+      T lo, di, up;
+      bool masked;
+      cubic2_row(a.x, n, bc.start, bc.end, k, lo, di, up, masked);
+      const T rhs = cubic2_rhs(a, bc, base, col, k, masked);
+      const T den = di - lo * cprev;
+      cprev = up / den;
+      dprev = (rhs - lo * dprev) / den;
+      if (k >= s) a.out[base + (int64_t)k * a.inner] = dprev;
+    }
+    // value just past the chunk from a backward elimination through the right halo:
+    //   x_e = dq - aq x_{e-1}   and   x_{e-1} = d'_{e-1} - c'_{e-1} x_e
+    T xnext = T(0);
+    if (e < n) {
+      T aq = T(0), dq = T(0);
+      for (int k = min(n, e + kHalo) - 1; k >= e; --k) {
+        T lo, di, up;
+        bool masked;
+        cubic2_row(a.x, n, bc.start, bc.end, k, lo, di, up, masked);
+        const T rhs = cubic2_rhs(a, bc, base, col, k, masked);
+        const T den = di - up * aq;
+        aq = lo / den;
+        dq = (rhs - up * dq) / den;
+      }
+      xnext = (dq - aq * dprev) / (T(1) - aq * cprev);
+    }
+    for (int k = e - 1; k >= s; --k) {
+      xnext = a.out[base + (int64_t)k * a.inner] - ws[k] * xnext;
+      a.out[base + (int64_t)k * a.inner] = xnext;
+    }
+  }
+}
+
 // n == 2: both ends take the secant when not-a-knot (_fd_derivs.py:175-179), then the
 // 2x2 system is solved by the same recurrence.  n == 3 with two not-a-knots: the parabola
 // through the three points, a dense 3x3 solve with partial pivoting (:185-203).
@@ -465,8 +547,14 @@ static int launch_slopes(const T* x, int32_t n, const T* f, int64_t outer, int64
       } else {
         if (workspace == nullptr) return IPX_EINVAL;
         T* ws = static_cast<T*>(workspace);
-        cubic2_factor_kernel<T><<<1, 32, 0, s>>>(x, n, bc.start, bc.end, ws);
-        cubic2_solve_kernel<T><<<cgrid, kSlopeThreads, 0, s>>>(a, bc, ws);
+        if (n > 4 * kChunk) {
+          const int chunks = (n + kChunk - 1) / kChunk;
+          cubic2_wfactor_kernel<T><<<(chunks + 127) / 128, 128, 0, s>>>(x, n, bc.start, bc.end, ws);
+          cubic2_wsolve_kernel<T><<<slope_grid(outer * inner * chunks), kSlopeThreads, 0, s>>>(a, bc, ws);
+        } else {
+          cubic2_factor_kernel<T><<<1, 32, 0, s>>>(x, n, bc.start, bc.end, ws);
+          cubic2_solve_kernel<T><<<cgrid, kSlopeThreads, 0, s>>>(a, bc, ws);
+        }
       }
       break;
     }

@@ -675,3 +675,25 @@ def test_wide_batch_1d_rows_kernel(B, dtype):
             assert_parity(got_c, want_c, "cls " + what, truth_c)
     res, idx = api._interp(1, (q_rand,), (x,), f, "cubic", 0, True, None, {}, return_index=True)
     assert np.array_equal(idx[0], O.bin_index(x, q_rand))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_cubic2_long_axis_windowed_solve(dtype):
+    """Axes longer than 1024 knots use the windowed Thomas solve (chunks of 256 rows entered
+    through 64-row halos); it must agree with the sequential sweep of the oracle to rounding,
+    for every boundary-condition kind, uniform and non-uniform knots, any table layout."""
+    rng = np.random.default_rng(11)
+    for n, shape, axis in [(1500, (1500,), 0), (4099, (4099, 3), 0), (2048, (2, 2048), 1), (1025, (2, 1025, 3), 1)]:
+        for uniform in (True, False):
+            x = (np.linspace(0, 5, n) if uniform else knots_nonuniform(rng, n, 0, 5, np.float64)).astype(dtype)
+            f = np.cumsum(rng.normal(size=shape), axis=axis).astype(dtype) * dtype(0.1)
+            vshape = tuple(sh for k, sh in enumerate(shape) if k != axis)
+            v1 = rng.normal(size=vshape).astype(dtype)
+            for bc in ("not-a-knot", "natural", "clamped", ((1, v1), "not-a-knot"), ("natural", (2, v1))):
+                want = O.approx_df(x, f, "cubic2", axis, bc_type=bc)
+                got = ipx.approx_df(x, f, "cubic2", axis, bc_type=bc)
+                truth = None
+                if dtype == np.float32:
+                    bc64 = bc if isinstance(bc, str) else tuple(b if isinstance(b, str) else (b[0], b[1].astype(np.float64)) for b in bc)
+                    truth = O.approx_df(x.astype(np.float64), f.astype(np.float64), "cubic2", axis, bc_type=bc64)
+                assert_parity(got, want.astype(dtype), f"n={n} {shape} uniform={uniform} bc={bc if isinstance(bc, str) else 'mixed'}", truth)
