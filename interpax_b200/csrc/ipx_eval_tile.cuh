@@ -34,7 +34,7 @@ namespace ipx {
 constexpr int kTileThreads = 256;
 constexpr int kTileWarps = kTileThreads / 32;
 constexpr int kMaxGroups = 4;       // more distinct columns than this in a warp -> direct path
-constexpr int kSmemKnotCap = 3072;  // total knots (all axes) staged in shared memory
+constexpr int kSmemKnotCap = 6144;  // total knots (all axes) staged in shared memory
 
 // RC = nodes of one run held per column (16: dense queries, several per cell; 32: sparse ones)
 template <typename T, int ND, int RC = 16> struct TileCfg {
