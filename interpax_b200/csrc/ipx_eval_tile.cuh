@@ -165,7 +165,11 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
   const unsigned cdst0 = tile_s + (ccol * kRunCap + cnode0) * Cfg::STRIDE + 16 * cpart;
 
   // ---- one located query -------------------------------------------------------------
-  auto locate_q = [&](const T (&qraw)[ND], QState<T, ND>& S, int& pz) {
+  // `cell` carries the located interval of the lane's first query ({x0, x1, 1/dx} per axis) to
+  // its second one: neighbours in a sorted stream are usually in the same interval, and then
+  // two comparisons replace the search (the result is the same interval by definition).
+  auto locate_q = [&](const T (&qraw)[ND], QState<T, ND>& S, int& pz, T (&cell)[ND][3],
+                      const QState<T, ND>* first) {
     S.fill = 0;
 #pragma unroll
     for (int ax = 0; ax < ND; ++ax) {
@@ -173,10 +177,10 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
       T q = qraw[ax];
       if (A.wrap) {
         const T Pd = T(fabs(P.axis[ax].period));
-        T r = q;
-        r = q < T(0) ? q + Pd : r;      // [-P,0): fmod leaves q, the sign fix adds P
-        r = q >= Pd ? q - Pd : r;       // [P,2P]: exact (Sterbenz)
-        if (!(q >= -Pd && q <= Pd + Pd)) r = py_mod_slow(q, Pd);  // anything else: exact remainder
+        // [-P,0): fmod leaves q and the sign fix adds P;  [P,2P): q - P is exact (Sterbenz);
+        // anything that does not land in [0,P) takes the exact remainder
+        T r = q < T(0) ? q + Pd : (q >= Pd ? q - Pd : q);
+        if (!(r >= T(0) && r < Pd)) r = py_mod_slow(q, Pd);
         q = r;
       }
       const int nk = A.nk;
@@ -184,17 +188,26 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
 #pragma unroll
       for (int k = 0; k < ax; ++k) koff += 2 * a.ax[k].nk;
       const T* ks = smT + koff;
-      const T xf = AX[ax].x_first, ih = AX[ax].inv_h;
-      int i = min(max(t_floor_to_int((q - xf) * ih), 0), nk - 2) + 1;
-      T lo = ks[i - 1], hi = ks[i];
-      // exact check of the guess against the knots (NaN fails it); the rare miss re-searches
-      if (!((q >= lo || i == 1) && (q < hi || i == nk - 1))) {
-        i = bin_index_slow(ks, nk, q, xf, ih);
-        lo = ks[i - 1];
-        hi = ks[i];
+      const T xf = AX[ax].x_first;
+      int i;
+      T lo, hi, dxi;
+      if (first != nullptr && q >= cell[ax][0] && q < cell[ax][1]) {
+        i = first->li[ax]; lo = cell[ax][0]; hi = cell[ax][1]; dxi = cell[ax][2];
+      } else {
+        const T ih = AX[ax].inv_h;
+        i = min(max(t_floor_to_int((q - xf) * ih), 0), nk - 2) + 1;
+        lo = ks[i - 1]; hi = ks[i];
+        // exact check of the guess against the knots (NaN fails it); the rare miss re-searches
+        if (!((q >= lo || i == 1) && (q < hi || i == nk - 1))) {
+          i = bin_index_slow(ks, nk, q, xf, ih);
+          lo = ks[i - 1];
+          hi = ks[i];
+        }
+        dxi = ks[nk + i];
       }
+      if (first == nullptr) { cell[ax][0] = lo; cell[ax][1] = hi; cell[ax][2] = dxi; }
       S.li[ax] = i;
-      hermite_weights_r<T, ORD0>(q, lo, hi, P.axis[ax].derivative, ks[nk + i], S.w[ax]);
+      hermite_weights_r<T, ORD0>(q, lo, hi, P.axis[ax].derivative, dxi, S.w[ax]);
       if (!A.wrap) {
         const ipx_axis_params& pa = P.axis[ax];
         if (!pa.keep_lo && q < xf) S.fill |= 1u << (2 * ax);
@@ -309,8 +322,11 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
 
     QState<T, ND> Sa, Sb;
     int pza, pzb;
-    locate_q(qc[0], Sa, pza);
-    locate_q(qc[1], Sb, pzb);
+    {
+      T cell[ND][3];
+      locate_q(qc[0], Sa, pza, cell, nullptr);
+      locate_q(qc[1], Sb, pzb, cell, &Sa);
+    }
 
     bool key_ok = true;
     unsigned ka = column_key(Sa, key_ok);
