@@ -341,6 +341,11 @@ def run_ours(args):
     launches += steps
     ms_random = timed(lambda: ip(*rq), steps, warmup)
     launches += steps
+    # the same random-order queries with the device-side spatial pre-sort (radix sort of cell
+    # keys, gather, evaluate, scatter -- all inside the timed region)
+    sort_launches = 2 + 5 * 3 + 3 + 1 + 1  # keys + 3 radix passes x 5 kernels (+copy) + gathers + eval + scatter
+    ms_presort = timed(lambda: ip(*rq, presort=True), max(3, steps // 2), 3)
+    launches += max(3, steps // 2) * sort_launches
 
     # ---- spot parity of what was just timed (first 4096 sorted queries), rank 0 ----
     parity = None
@@ -444,6 +449,9 @@ def run_ours(args):
                          "roofline_frac": ach_random / peak,
                          "note": "random queries on a 1.07 GB table are bound by DRAM sector traffic "
                                  "(>=512 B/query), not by the algorithmic bytes"},
+        "random_order_presorted": {"value": world * nq / (ms_presort * 1e-3), "ms_per_step": ms_presort,
+                                   "note": "same random-order queries, Interpolator3D(..., presort=True): "
+                                           "cell-key radix sort + gather + evaluate + scatter, all timed"},
         "e2e": e2e,
         "gpu_launches": launches,
         "clocks": sampler.summary(),

@@ -196,6 +196,32 @@ int ipx_pack_f32(int32_t ndim, const float* const* tables, int64_t nodes_times_b
 int ipx_pack_f64(int32_t ndim, const double* const* tables, int64_t nodes_times_batch,
                  double* out, void* stream);
 
+/* ---------------------------------------------------------------------------------
+ * Spatial pre-sort of the query stream (no counterpart in the reference, which evaluates
+ * queries in the order given, interpax/_spline.py:1051-1099).
+ * ipx_cell_order_*: order[k] = index of the k-th query in cell order (stable argsort of the
+ * linear cell key built from the same interval lookup as the evaluation).  q / knots are
+ * HOST arrays of ndim device pointers, n the table extents, periodic_mask / params as for
+ * ipx_eval*.  nq < 2^32, number of cells < 2^32.  workspace: ipx_cell_order_workspace_bytes(nq).
+ * ipx_gather_*:  dst[k*batch + b] = src[order[k]*batch + b];  ipx_scatter_*: the inverse.
+ * A caller evaluates  scatter(eval(gather(q)))  and gets bit-identical results to eval(q).
+ * --------------------------------------------------------------------------------- */
+size_t ipx_cell_order_workspace_bytes(int64_t nq);
+int ipx_cell_order_f32(int32_t ndim, const float* const* q, int64_t nq, const float* const* knots,
+                       const int32_t* n, int32_t periodic_mask, const ipx_params* params,
+                       int32_t params_on_device, uint32_t* order, void* workspace, void* stream);
+int ipx_cell_order_f64(int32_t ndim, const double* const* q, int64_t nq, const double* const* knots,
+                       const int32_t* n, int32_t periodic_mask, const ipx_params* params,
+                       int32_t params_on_device, uint32_t* order, void* workspace, void* stream);
+int ipx_gather_f32(const float* src, const uint32_t* order, int64_t n, int64_t batch, float* dst,
+                   void* stream);
+int ipx_gather_f64(const double* src, const uint32_t* order, int64_t n, int64_t batch, double* dst,
+                   void* stream);
+int ipx_scatter_f32(const float* src, const uint32_t* order, int64_t n, int64_t batch, float* dst,
+                    void* stream);
+int ipx_scatter_f64(const double* src, const uint32_t* order, int64_t n, int64_t batch, double* dst,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

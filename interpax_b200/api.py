@@ -297,6 +297,51 @@ def _pack_dev(ndim: int, tabs: list[torch.Tensor]) -> torch.Tensor:
     return out
 
 
+def _cell_order_dev(ndim, qs, knots, ns, periodic_mask, params) -> torch.Tensor:
+    """Visiting order of the queries by table cell (stable argsort of the linear cell index)."""
+    lib = L.load()
+    nq = qs[0].numel()
+    order = torch.empty(nq, dtype=torch.int32, device=qs[0].device)  # holds uint32 values
+    ws = torch.empty(max(int(lib.ipx_cell_order_workspace_bytes(nq)), 256), dtype=torch.uint8,
+                     device=qs[0].device)
+    fn = getattr(lib, f"ipx_cell_order_{_suffix(qs[0])}")
+    narr = (C.c_int32 * ndim)(*[int(n) for n in ns])
+    L.check(fn(ndim, _ptr_array(qs), nq, _ptr_array(knots), narr, periodic_mask, C.byref(params), 0,
+               _ptr(order), _ptr(ws), _stream()), "ipx_cell_order")
+    return order
+
+
+def _permute_dev(src: torch.Tensor, order: torch.Tensor, batch: int, gather: bool,
+                 dst: torch.Tensor | None = None) -> torch.Tensor:
+    lib = L.load()
+    n = order.numel()
+    if dst is None:
+        dst = torch.empty_like(src)
+    fn = getattr(lib, f"ipx_{'gather' if gather else 'scatter'}_{_suffix(src)}")
+    L.check(fn(_ptr(src), _ptr(order), n, batch, _ptr(dst), _stream()), "ipx_gather/scatter")
+    return dst
+
+
+def _presorted(launch, ndim, knots, ns, mask, params, batch):
+    """Wrap `launch` so that it visits the queries in cell order: gather -> evaluate -> scatter
+    (results are bit-identical to the plain call; only the memory access pattern changes)."""
+
+    def run(dq, dout, want_idx):
+        errorif(want_idx, NotImplementedError, "interval indices are not available with presort")
+        nq = dq[0].numel()
+        if nq == 0:
+            return launch(dq, dout, False)
+        order = _cell_order_dev(ndim, dq, knots, ns, mask, params)
+        qs = [_permute_dev(q, order, 1, True) for q in dq]
+        tmp, _ = launch(qs, None, False)
+        if dout is None:
+            dout = torch.empty((nq, batch), dtype=tmp.dtype, device=tmp.device)
+        _permute_dev(tmp, order, batch, False, dout)
+        return dout, None
+
+    return run
+
+
 def _make_params(ndim, derivative, extrap6, periods) -> L.Params:
     p = L.Params()
     for ax in range(ndim):
@@ -496,6 +541,7 @@ def _interp(ndim, qs, knots, f, method, derivative, extrap, period, kwargs, retu
     kwargs = dict(kwargs)
     given = {n: kwargs.pop(n, None) for n in names[1:]}
     out_arg = kwargs.pop("out", None)
+    presort = bool(kwargs.pop("presort", False))
     if ndim == 1:
         axis = kwargs.get("axis", 0)
         errorif(axis != 0, NotImplementedError, "only axis=0 is supported")
@@ -566,6 +612,8 @@ def _interp(ndim, qs, knots, f, method, derivative, extrap, period, kwargs, retu
         return _eval_dev(ndim, dq, kuse, perms, ns, tables, L.IPX_SOA, batch, mclass, mask, params,
                          want_idx, dout)
 
+    if presort:
+        launch = _presorted(launch, ndim, kuse, ns, mask, params, batch)
     return _execute(io, qs, launch, batch, fshape_user[ndim:], out_arg, return_index)
 
 
@@ -701,7 +749,7 @@ class _InterpolatorND:
             self._pk_cache[key] = (xpad, perm)
         return self._pk_cache[key]
 
-    def _call(self, qs, derivative, out=None, return_index=False):
+    def _call(self, qs, derivative, out=None, return_index=False, presort=False):
         ndim = self._ndim
         st = self._io
         # promotion of the call mirrors interpNd(xq, self.x, self.f, ...)
@@ -712,6 +760,8 @@ class _InterpolatorND:
             kw = {n: self._user(self._tabs[n]) for n in TABLES[ndim][1:]}
             if out is not None:
                 kw["out"] = out
+            if presort:
+                kw["presort"] = True
             res = _interp(ndim, qs, [k for k in self._knots], self._user(self._tabs["f"]),
                           self.method, derivative, self.extrap, self.period, kw, return_index)
             if io.want_torch:
@@ -741,13 +791,18 @@ class _InterpolatorND:
             return _eval_dev(ndim, dq, kuse, perms, ns, tables, layout, batch, mclass, mask, params,
                              want_idx, dout)
 
+        if presort:
+            launch = _presorted(launch, ndim, kuse, ns, mask, params, batch)
         return _execute(io, qs, launch, batch, self._fshape[ndim:], out, return_index)
 
 
 class Interpolator1D(_InterpolatorND):
     """Convenience class for a 1D interpolated function; same contract as
-    interpax.Interpolator1D (_spline.py:48-150).  ``out=`` (optional, an extension) is a
-    preallocated result tensor, e.g. pinned host memory for host-resident queries."""
+    interpax.Interpolator1D (_spline.py:48-150).  Two optional extensions of ``__call__``:
+    ``out=`` a preallocated result tensor (e.g. pinned host memory for host-resident queries);
+    ``presort=True`` visits the queries in table-cell order (device-side radix sort, gather,
+    evaluate, scatter) -- same results bit for bit, much faster for random-order queries on
+    tables larger than L2."""
 
     _ndim = 1
 
@@ -758,8 +813,8 @@ class Interpolator1D(_InterpolatorND):
     def x(self):
         return self._knots[0]
 
-    def __call__(self, xq, dx=0, out=None):
-        return self._call((xq,), (dx,), out)
+    def __call__(self, xq, dx=0, out=None, presort=False):
+        return self._call((xq,), (dx,), out, presort=presort)
 
 
 class Interpolator2D(_InterpolatorND):
@@ -778,8 +833,8 @@ class Interpolator2D(_InterpolatorND):
     def y(self):
         return self._knots[1]
 
-    def __call__(self, xq, yq, dx=0, dy=0, out=None):
-        return self._call((xq, yq), (dx, dy), out)
+    def __call__(self, xq, yq, dx=0, dy=0, out=None, presort=False):
+        return self._call((xq, yq), (dx, dy), out, presort=presort)
 
 
 class Interpolator3D(_InterpolatorND):
@@ -802,5 +857,5 @@ class Interpolator3D(_InterpolatorND):
     def z(self):
         return self._knots[2]
 
-    def __call__(self, xq, yq, zq, dx=0, dy=0, dz=0, out=None):
-        return self._call((xq, yq, zq), (dx, dy, dz), out)
+    def __call__(self, xq, yq, zq, dx=0, dy=0, dz=0, out=None, presort=False):
+        return self._call((xq, yq, zq), (dx, dy, dz), out, presort=presort)
