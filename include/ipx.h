@@ -217,6 +217,11 @@ int ipx_gather_f32(const float* src, const uint32_t* order, int64_t n, int64_t b
                    void* stream);
 int ipx_gather_f64(const double* src, const uint32_t* order, int64_t n, int64_t batch, double* dst,
                    void* stream);
+/* up to 3 arrays at once (the query coordinates): dst[a][k] = src[a][order[k]] */
+int ipx_gather_multi_f32(int32_t narrays, const float* const* src, const uint32_t* order, int64_t n,
+                         float* const* dst, void* stream);
+int ipx_gather_multi_f64(int32_t narrays, const double* const* src, const uint32_t* order, int64_t n,
+                         double* const* dst, void* stream);
 int ipx_scatter_f32(const float* src, const uint32_t* order, int64_t n, int64_t batch, float* dst,
                     void* stream);
 int ipx_scatter_f64(const double* src, const uint32_t* order, int64_t n, int64_t batch, double* dst,

@@ -332,7 +332,10 @@ def _presorted(launch, ndim, knots, ns, mask, params, batch):
         if nq == 0:
             return launch(dq, dout, False)
         order = _cell_order_dev(ndim, dq, knots, ns, mask, params)
-        qs = [_permute_dev(q, order, 1, True) for q in dq]
+        qs = [torch.empty_like(q) for q in dq]
+        lib = L.load()
+        fn = getattr(lib, f"ipx_gather_multi_{_suffix(dq[0])}")
+        L.check(fn(ndim, _ptr_array(dq), _ptr(order), nq, _ptr_array(qs), _stream()), "ipx_gather_multi")
         tmp, _ = launch(qs, None, False)
         if dout is None:
             dout = torch.empty((nq, batch), dtype=tmp.dtype, device=tmp.device)

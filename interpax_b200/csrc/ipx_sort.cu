@@ -41,7 +41,9 @@ static int sm_count() {
 // ---------------------------------------------------------------------------------- keys
 template <typename T, int ND> struct KeyArgs {
   AxisDesc<T> ax[ND];
-  uint32_t stride[ND];  // key = sum (i_ax - 1) * stride[ax]; last axis has stride 1
+  uint32_t stride[ND];  // key = sum cell_ax * stride[ax]; last axis has stride 1
+  uint32_t cells[ND];   // cells along the axis; on a periodic axis the padded intervals 1 and
+                        // n+1 are the same physical cell (the seam) and share a key digit
   int64_t nq;
   ipx_params hp;
   const ipx_params* dp;
@@ -62,7 +64,9 @@ __global__ void cell_key_kernel(const KeyArgs<T, ND> a, uint32_t* __restrict__ k
     for (int ax = 0; ax < ND; ++ax) {
       AxisLoc<T> L;
       locate(a.ax[ax], consts[ax], params_s.axis[ax], e, L);
-      key += (uint32_t)(L.i - 1) * a.stride[ax];
+      uint32_t c = (uint32_t)(L.i - 1);
+      if (c >= a.cells[ax]) c -= a.cells[ax];
+      key += c * a.stride[ax];
     }
     keys[e] = key;
     vals[e] = (uint32_t)e;
@@ -160,18 +164,27 @@ __global__ void scan_add_kernel(uint32_t* __restrict__ data, int64_t count, cons
 }
 
 // stable scatter of one tile per block.  Warp w owns items [w*512, (w+1)*512) of the tile and
-// walks them 32 at a time in order, so rank-within-warp preserves the input order.
-__global__ void radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                                     int64_t n, int shift, const uint32_t* __restrict__ offsets, int nblocks,
-                                     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+// walks them 32 at a time in order, so rank-within-warp preserves the input order.  Items are
+// first placed in shared memory in digit order, then written out: consecutive threads write
+// consecutive addresses of a digit's run instead of 32 scattered words per warp.
+__global__ void __launch_bounds__(kSortThreads)
+radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, int64_t n,
+                     int shift, const uint32_t* __restrict__ offsets, int nblocks,
+                     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
   constexpr int kWarps = kSortThreads / 32;
   constexpr int kPerWarp = kSortTile / kWarps;  // 512
   constexpr int kSteps = kPerWarp / 32;         // 16
-  __shared__ uint32_t wcount[kWarps][kRadix];   // per-warp digit counts, then exclusive bases
+  static_assert(kRadix == kSortThreads, "one thread per digit in the prefix step");
+  __shared__ uint32_t wcount[kWarps][kRadix];   // per-warp digit counts, then warp-exclusive bases
+  __shared__ uint32_t dbase[kRadix];            // block-local exclusive base of each digit
+  __shared__ uint32_t gbase[kRadix];            // global position of the digit's run minus dbase
+  __shared__ uint32_t skeys[kSortTile];
+  __shared__ uint32_t svals[kSortTile];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int d = lane; d < kRadix; d += 32) wcount[warp][d] = 0;
   __syncwarp();
-  const int64_t wbase = (int64_t)blockIdx.x * kSortTile + (int64_t)warp * kPerWarp;
+  const int64_t tbase = (int64_t)blockIdx.x * kSortTile;
+  const int64_t wbase = tbase + (int64_t)warp * kPerWarp;
   uint32_t key[kSteps], val[kSteps];
   uint16_t rank[kSteps];
 #pragma unroll
@@ -184,24 +197,26 @@ __global__ void radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const
     const unsigned peers = __match_any_sync(0xffffffffu, d);
     const unsigned before = __popc(peers & ((1u << lane) - 1));
     uint32_t basecnt = 0;
-    if (ok) {
-      basecnt = wcount[warp][d];  // all peers read the same value before the leader bumps it
-    }
+    if (ok) basecnt = wcount[warp][d];  // all peers read the same value before the leader bumps it
     __syncwarp();
     if (ok && before == 0) wcount[warp][d] = basecnt + __popc(peers);
     __syncwarp();
     rank[s] = (uint16_t)(basecnt + before);
   }
   __syncthreads();
-  // exclusive prefix over warps for every digit, plus the block's global offset
-  for (int d = threadIdx.x; d < kRadix; d += kSortThreads) {
-    uint32_t run = offsets[(int64_t)d * nblocks + blockIdx.x];
+  // one thread per digit: warp-exclusive bases, digit total, block-exclusive digit base
+  {
+    const int d = threadIdx.x;
+    uint32_t run = 0;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) {
       const uint32_t c = wcount[w][d];
       wcount[w][d] = run;
       run += c;
     }
+    const uint32_t excl = block_exclusive_scan(run, nullptr);
+    dbase[d] = excl;
+    gbase[d] = offsets[(int64_t)d * nblocks + blockIdx.x] - excl;
   }
   __syncthreads();
 #pragma unroll
@@ -209,10 +224,18 @@ __global__ void radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const
     const int64_t e = wbase + s * 32 + lane;
     if (e < n) {
       const unsigned d = (key[s] >> shift) & (kRadix - 1);
-      const uint32_t pos = wcount[warp][d] + rank[s];
-      keys_out[pos] = key[s];
-      vals_out[pos] = val[s];
+      const uint32_t local = dbase[d] + wcount[warp][d] + rank[s];
+      skeys[local] = key[s];
+      svals[local] = val[s];
     }
+  }
+  __syncthreads();
+  const int count = (int)min((int64_t)kSortTile, n - tbase);
+  for (int i = threadIdx.x; i < count; i += kSortThreads) {
+    const uint32_t k = skeys[i];
+    const uint32_t pos = gbase[(k >> shift) & (kRadix - 1)] + (uint32_t)i;
+    keys_out[pos] = k;
+    vals_out[pos] = svals[i];
   }
 }
 
@@ -280,13 +303,14 @@ static int launch_cell_order(const T* const* q, int64_t nq, const T* const* knot
     a.ax[ax].nk = per ? n[ax] + 2 : n[ax];
     a.ax[ax].periodic = 0;
     a.ax[ax].wrap = per | wrap_only;
-    cells *= (double)(a.ax[ax].nk - 1);
+    a.cells[ax] = (uint32_t)(per ? n[ax] : n[ax] - 1);
+    cells *= (double)a.cells[ax];
   }
   if (cells >= 4294967296.0) return IPX_EUNSUPPORTED;
   uint32_t stride = 1;
   for (int ax = ND - 1; ax >= 0; --ax) {
     a.stride[ax] = stride;
-    stride *= (uint32_t)(a.ax[ax].nk - 1);
+    stride *= a.cells[ax];
   }
   int bits = 1;
   while (bits < 32 && (double)(1ull << bits) < cells) ++bits;
@@ -329,6 +353,53 @@ __global__ void scatter_kernel(const T* __restrict__ src, const uint32_t* __rest
     const int64_t b = e - k * batch;
     dst[(int64_t)order[k] * batch + b] = src[e];
   }
+}
+
+template <typename T, int NA> struct MultiArgs {
+  const T* __restrict__ src[NA];
+  T* __restrict__ dst[NA];
+};
+
+// dst[a][k] = src[a][order[k]] for NA arrays at once: the order is read once and the NA random
+// loads of a thread are in flight together
+template <typename T, int NA>
+__global__ void gather_multi_kernel(const MultiArgs<T, NA> a, const uint32_t* __restrict__ order, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+    const uint32_t o = order[k];
+    T v[NA];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) v[i] = a.src[i][o];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) a.dst[i][k] = v[i];
+  }
+}
+
+template <typename T, int NA>
+static int launch_gather_multi_n(const T* const* src, const uint32_t* order, int64_t n, T* const* dst,
+                                 cudaStream_t s) {
+  MultiArgs<T, NA> a;
+  for (int i = 0; i < NA; ++i) {
+    if (src[i] == nullptr || dst[i] == nullptr) return IPX_EINVAL;
+    a.src[i] = src[i];
+    a.dst[i] = dst[i];
+  }
+  int64_t need = (n + 255) / 256;
+  int64_t cap = (int64_t)sm_count() * 32;
+  gather_multi_kernel<T, NA><<<(int)(need < cap ? need : cap), 256, 0, s>>>(a, order, n);
+  return cudaPeekAtLastError() == cudaSuccess ? IPX_OK : IPX_ELAUNCH;
+}
+
+template <typename T>
+static int launch_gather_multi(int32_t narrays, const T* const* src, const uint32_t* order, int64_t n,
+                               T* const* dst, void* stream) {
+  if (narrays < 1 || narrays > 3 || src == nullptr || dst == nullptr || n < 0) return IPX_EINVAL;
+  if (n == 0) return IPX_OK;
+  if (order == nullptr) return IPX_EINVAL;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (narrays == 1) return launch_gather_multi_n<T, 1>(src, order, n, dst, s);
+  if (narrays == 2) return launch_gather_multi_n<T, 2>(src, order, n, dst, s);
+  return launch_gather_multi_n<T, 3>(src, order, n, dst, s);
 }
 
 template <typename T, bool GATHER>
@@ -384,6 +455,14 @@ extern "C" int ipx_gather_f32(const float* src, const uint32_t* order, int64_t n
 extern "C" int ipx_gather_f64(const double* src, const uint32_t* order, int64_t n, int64_t batch, double* dst,
                               void* stream) {
   return ipx::launch_permute<double, true>(src, order, n, batch, dst, stream);
+}
+extern "C" int ipx_gather_multi_f32(int32_t narrays, const float* const* src, const uint32_t* order, int64_t n,
+                                    float* const* dst, void* stream) {
+  return ipx::launch_gather_multi<float>(narrays, src, order, n, dst, stream);
+}
+extern "C" int ipx_gather_multi_f64(int32_t narrays, const double* const* src, const uint32_t* order,
+                                    int64_t n, double* const* dst, void* stream) {
+  return ipx::launch_gather_multi<double>(narrays, src, order, n, dst, stream);
 }
 extern "C" int ipx_scatter_f32(const float* src, const uint32_t* order, int64_t n, int64_t batch, float* dst,
                                void* stream) {
