@@ -102,7 +102,7 @@ template <typename T, int ND> struct QState {
 };
 
 __device__ __forceinline__ void cp_async16_s(unsigned smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.wait_all;\n" ::: "memory");
@@ -276,7 +276,7 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
         if (S.fill & (2u << (2 * ax))) res = T(P.axis[ax].fill_hi);
       }
     }
-    a.out[qi] = res;
+    __stcs(a.out + qi, res);
     if (want_idx) {
 #pragma unroll
       for (int ax = 0; ax < ND; ++ax) a.idx_out[(int64_t)ax * a.nq + qi] = S.li[ax];
@@ -296,10 +296,10 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
     for (int ax = 0; ax < ND; ++ax) {
       if (q + 1 < a.nq) {  // q is even and the arrays are 16-byte aligned: one vector load
         if (sizeof(T) == 8) {
-          const double2 v = *reinterpret_cast<const double2*>(a.ax[ax].q + q);
+          const double2 v = __ldcs(reinterpret_cast<const double2*>(a.ax[ax].q + q));
           qn[0][ax] = T(v.x); qn[1][ax] = T(v.y);
         } else {
-          const float2 v = *reinterpret_cast<const float2*>(a.ax[ax].q + q);
+          const float2 v = __ldcs(reinterpret_cast<const float2*>(a.ax[ax].q + q));
           qn[0][ax] = T(v.x); qn[1][ax] = T(v.y);
         }
       } else {
