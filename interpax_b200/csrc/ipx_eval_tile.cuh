@@ -228,6 +228,111 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
     pz = S.li[ND - 1] - 1;
   };
 
+  // ---- locate both queries of the lane ---------------------------------------------------
+  // Written as three straight-line phases so that the 2 x ND independent dependency chains
+  // (wrap -> guess -> knot loads -> check -> weights) interleave instead of running one after
+  // the other: (A) wrap, guess and knot loads for every (query, axis) with the exceptional
+  // cases only FLAGGED; (B) one branch that repairs flagged entries (rare: |q| beyond one
+  // period, a guess off by a cell, NaN); (C) weights, fill flags and corner indices.
+  // Used in 1-D / 2-D; in 3-D holding all chains at once exceeds the 128-register budget and
+  // the sequential locate_q above (with interval reuse for the second query) is faster.
+  auto locate_range = [&](const T (&qraw)[2][ND], QState<T, ND> (&S)[2], int (&pz)[2], const int k_lo,
+                          const int k_hi) {
+    T q[2][ND], lo[2][ND], hi[2][ND], dxi[2][ND];
+    int ii[2][ND];
+    unsigned bad = 0;  // bit 2*ax + k set: entry (k, ax) needs the slow path
+    // (A)
+#pragma unroll
+    for (int ax = 0; ax < ND; ++ax) {
+      const AxisDesc<T>& A = a.ax[ax];
+      const int nk = A.nk;
+      int koff = 0;
+#pragma unroll
+      for (int k = 0; k < ax; ++k) koff += 2 * a.ax[k].nk;
+      const T* ks = smT + koff;
+      const T xf = AX[ax].x_first, ih = AX[ax].inv_h;
+      const T Pd = T(fabs(P.axis[ax].period));
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (k < k_lo || k >= k_hi) continue;
+        T v = qraw[k][ax];
+        // [-P,0): fmod leaves q and the sign fix adds P;  [P,2P): q - P is exact (Sterbenz)
+        const T r = v < T(0) ? v + Pd : (v >= Pd ? v - Pd : v);
+        const bool wrap_bad = A.wrap && !(r >= T(0) && r < Pd);
+        v = A.wrap ? r : v;
+        const int i = min(max(t_floor_to_int((v - xf) * ih), 0), nk - 2) + 1;
+        const T l = ks[i - 1], h = ks[i];
+        // exact check of the guess against the knots; NaN fails it
+        const bool ok = (v >= l || i == 1) && (v < h || i == nk - 1);
+        if (wrap_bad || !ok) bad |= 1u << (2 * ax + k);
+        q[k][ax] = v; lo[k][ax] = l; hi[k][ax] = h; ii[k][ax] = i;
+        dxi[k][ax] = ks[nk + i];
+      }
+    }
+    // (B)
+    if (bad) {
+#pragma unroll
+      for (int ax = 0; ax < ND; ++ax) {
+        const AxisDesc<T>& A = a.ax[ax];
+        const int nk = A.nk;
+        int koff = 0;
+#pragma unroll
+        for (int k = 0; k < ax; ++k) koff += 2 * a.ax[k].nk;
+        const T* ks = smT + koff;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (k < k_lo || k >= k_hi) continue;
+          if (bad & (1u << (2 * ax + k))) {
+            T v = qraw[k][ax];
+            if (A.wrap) v = py_mod_slow(v, T(fabs(P.axis[ax].period)));
+            const int i = bin_index_slow(ks, nk, v, AX[ax].x_first, AX[ax].inv_h);
+            q[k][ax] = v; ii[k][ax] = i;
+            lo[k][ax] = ks[i - 1]; hi[k][ax] = ks[i]; dxi[k][ax] = ks[nk + i];
+          }
+        }
+      }
+    }
+    // (C)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (k < k_lo || k >= k_hi) continue;
+      S[k].fill = 0;
+#pragma unroll
+      for (int ax = 0; ax < ND; ++ax) {
+        const AxisDesc<T>& A = a.ax[ax];
+        const int i = ii[k][ax];
+        S[k].li[ax] = i;
+        hermite_weights_r<T, ORD0>(q[k][ax], lo[k][ax], hi[k][ax], P.axis[ax].derivative, dxi[k][ax],
+                                   S[k].w[ax]);
+        const ipx_axis_params& pa = P.axis[ax];
+        const bool flo = !A.wrap && !pa.keep_lo && q[k][ax] < AX[ax].x_first;
+        const bool fhi = !A.wrap && !pa.keep_hi && q[k][ax] > AX[ax].x_last;
+        S[k].fill |= (flo ? 1u : 0u) << (2 * ax);
+        S[k].fill |= (fhi ? 2u : 0u) << (2 * ax);
+        if (ax < ND - 1) {
+          int s0 = i - 2; s0 += s0 < 0 ? A.n : 0;
+          int s1 = i - 1; s1 -= s1 >= A.n ? A.n : 0;
+          S[k].t0[ax] = A.periodic ? s0 : i - 1;
+          S[k].t1[ax] = A.periodic ? s1 : i;
+        }
+      }
+      pz[k] = S[k].li[ND - 1] - 1;
+    }
+    // un-sorted periodic knots: sorted position -> table index (rare; identity is passed as NULL)
+#pragma unroll
+    for (int ax = 0; ax < ND - 1; ++ax) {
+      const int32_t* pm = a.ax[ax].periodic ? a.ax[ax].perm : nullptr;
+      if (pm != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (k < k_lo || k >= k_hi) continue;
+          S[k].t0[ax] = pm[S[k].t0[ax]];
+          S[k].t1[ax] = pm[S[k].t1[ax]];
+        }
+      }
+    }
+  };
+
   auto column_key = [&](const QState<T, ND>& S, bool& ok) {
     unsigned key = 0;
 #pragma unroll
@@ -320,13 +425,18 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
       for (int ax = 0; ax < ND; ++ax) qc[k][ax] = qn[k][ax];
     if (round + 1 < rounds) prefetch(qa + step);
 
-    QState<T, ND> Sa, Sb;
-    int pza, pzb;
-    {
+    QState<T, ND> SS[2];
+    int pzz[2];
+    if constexpr (ND == 3) {
       T cell[ND][3];
-      locate_q(qc[0], Sa, pza, cell, nullptr);
-      locate_q(qc[1], Sb, pzb, cell, &Sa);
+      locate_q(qc[0], SS[0], pzz[0], cell, nullptr);
+      locate_q(qc[1], SS[1], pzz[1], cell, &SS[0]);
+    } else {
+      locate_range(qc, SS, pzz, 0, 2);
     }
+    QState<T, ND>& Sa = SS[0];
+    QState<T, ND>& Sb = SS[1];
+    const int pza = pzz[0], pzb = pzz[1];
 
     bool key_ok = true;
     unsigned ka = column_key(Sa, key_ok);
