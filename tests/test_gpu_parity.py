@@ -738,3 +738,35 @@ def test_presort_is_bitwise_identical(ndim):
     for ax in range(ndim):
         key = key * (ns[ax] - 1) + (O.bin_index(knots[ax], qs[ax]) - 1)
     assert np.array_equal(order, np.argsort(key, kind="stable"))
+
+
+def test_cuda_graph_capture_of_the_class_call():
+    """"jit" for the headline path: Interpolator3D.__call__ (tile kernel, periodic axes, packed
+    tables) captured in a CUDA graph and replayed on new query values."""
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(5)
+    n = 40
+    P = 2 * np.pi
+    x = torch.arange(n, device=dev, dtype=torch.float64) * (P / n)
+    z = torch.linspace(0, 1, n, device=dev, dtype=torch.float64)
+    f = torch.randn((n, n, n), dtype=torch.float64, device=dev, generator=g)
+    ip = ipx.Interpolator3D(x, x, z, f, "cubic", ((True, True), (True, True), (True, 0.0)), (P, P, None))
+    nq = 50_000
+    q = [(torch.rand(nq, dtype=torch.float64, device=dev, generator=g) * 3 - 1) * P for _ in range(2)]
+    q.append(torch.rand(nq, dtype=torch.float64, device=dev, generator=g) * 1.1 - 0.05)
+    out = torch.empty(nq, dtype=torch.float64, device=dev)
+    ip(*q, out=out)  # warm-up: builds the periodic-knot cache (one host sync), loads the kernel
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(graph, stream=s):
+            ip(*q, 1, 0, 0, out=out)
+    for _ in range(2):
+        for t in q[:2]:
+            t.copy_((torch.rand(nq, dtype=torch.float64, device=dev, generator=g) * 3 - 1) * P)
+        graph.replay()
+        torch.cuda.synchronize()
+        want = ip(*q, 1, 0, 0)
+        assert torch.equal(out, want)
