@@ -611,8 +611,16 @@ def _interp(ndim, qs, knots, f, method, derivative, extrap, period, kwargs, retu
     ns = [tabs["f"].shape[ax] for ax in range(ndim)]
     params = _make_params(ndim, derivs, ex, periods)
 
+    # Many queries on scalar-valued cubic tables: interleave the tables once (one pass over
+    # them) and use the tile kernel, as Interpolator* does; few queries: read the reference's
+    # separate tables in place.
+    layout = L.IPX_SOA
+    nq_total = int(np.prod([int(v) for v in np.broadcast_shapes(*[_shape(q) for q in qs])], dtype=np.int64))
+    if mclass == L.IPX_CUBIC and batch == 1 and 2 * nq_total >= tables[0].numel():
+        tables, layout = [_pack_dev(ndim, tables)], L.IPX_AOS
+
     def launch(dq, dout, want_idx):
-        return _eval_dev(ndim, dq, kuse, perms, ns, tables, L.IPX_SOA, batch, mclass, mask, params,
+        return _eval_dev(ndim, dq, kuse, perms, ns, tables, layout, batch, mclass, mask, params,
                          want_idx, dout)
 
     if presort:
