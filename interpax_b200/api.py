@@ -616,7 +616,7 @@ def _interp(ndim, qs, knots, f, method, derivative, extrap, period, kwargs, retu
     # separate tables in place.
     layout = L.IPX_SOA
     nq_total = int(np.prod([int(v) for v in np.broadcast_shapes(*[_shape(q) for q in qs])], dtype=np.int64))
-    if mclass == L.IPX_CUBIC and batch == 1 and 2 * nq_total >= tables[0].numel():
+    if mclass == L.IPX_CUBIC and batch == 1 and nq_total >= (1 << 16) and 2 * nq_total >= tables[0].numel():
         tables, layout = [_pack_dev(ndim, tables)], L.IPX_AOS
 
     def launch(dq, dout, want_idx):

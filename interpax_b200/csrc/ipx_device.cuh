@@ -41,12 +41,6 @@ __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(
 __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
 
-template <typename T> __device__ __forceinline__ T quiet_nan();
-template <> __device__ __forceinline__ float quiet_nan<float>() { return __int_as_float(0x7fc00000); }
-template <> __device__ __forceinline__ double quiet_nan<double>() {
-  return __longlong_as_double(0x7ff8000000000000LL);
-}
-
 // Python / jnp.remainder for a positive modulus: result in [0, P] with the sign of P.
 template <typename T> __device__ __forceinline__ T py_mod(T q, T P) {
   T r = t_fmod(q, P);
