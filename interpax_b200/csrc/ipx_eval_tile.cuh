@@ -111,7 +111,7 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // DEVP: traced operands are read from device memory.  ORD0: every derivative order is 0 (known
 // on the host when the operands are host-resident), which drops the order switch from the loop.
 template <typename T, int ND, bool DEVP, bool ORD0, int RC>
-__global__ void __launch_bounds__(kTileThreads, 2)
+__global__ void __launch_bounds__(kTileThreads, sizeof(T) == 4 ? 3 : 2)
 eval_tile_kernel(const EvalArgs<T, ND> a) {
   using Cfg = TileCfg<T, ND, RC>;
   constexpr int kRunCap = RC;
