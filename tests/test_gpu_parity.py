@@ -770,3 +770,31 @@ def test_cuda_graph_capture_of_the_class_call():
         torch.cuda.synchronize()
         want = ip(*q, 1, 0, 0)
         assert torch.equal(out, want)
+
+
+def test_more_than_2_to_31_queries():
+    """64-bit indexing: 2^31 + 37 queries through the tile kernel (1-D f64 cubic, class form)
+    and the generic kernel (1-D f32 linear); checked at the far end and at random positions
+    against the same calls on small slices."""
+    dev = torch.device("cuda")
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60 * 2**30:
+        pytest.skip("needs ~45 GB of free device memory")
+    nq = 2**31 + 37
+    n = 1000
+    x = torch.linspace(0, 1, n, dtype=torch.float64, device=dev)
+    f = torch.sin(7 * x)
+    ip = ipx.Interpolator1D(x, f, "cubic", True)
+    q = torch.empty(nq, dtype=torch.float64, device=dev)
+    q[:] = torch.linspace(-0.01, 1.01, 1 << 20, dtype=torch.float64, device=dev).repeat(nq // (1 << 20) + 1)[:nq]
+    out = torch.empty(nq, dtype=torch.float64, device=dev)
+    ip(q, out=out)
+    for lo in (0, 2**31 - 1000, nq - 4096):
+        assert torch.equal(out[lo:lo + 4096], ip(q[lo:lo + 4096].clone()))
+    del out
+    q32 = q.to(torch.float32)
+    del q
+    lin = ipx.interp1d(q32, x.to(torch.float32), f.to(torch.float32), "linear", 0, True)
+    for lo in (0, 2**31 + 5, nq - 4096):
+        want = ipx.interp1d(q32[lo:lo + 4096].clone(), x.to(torch.float32), f.to(torch.float32), "linear", 0, True)
+        assert torch.equal(lin[lo:lo + 4096][:want.numel()], want)
