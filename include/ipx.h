@@ -227,6 +227,26 @@ int ipx_scatter_f32(const float* src, const uint32_t* order, int64_t n, int64_t 
 int ipx_scatter_f64(const double* src, const uint32_t* order, int64_t n, int64_t batch, double* dst,
                     void* stream);
 
+/* ---------------------------------------------------------------------------------
+ * Reverse-mode rule with respect to the tables: grad_tables[ff][node, b] += cotangent[q, b] *
+ * d out[q, b] / d tables[ff][node, b] (accumulates: zero the gradients first).  This is the
+ * transpose of the gather + A @ F contraction that JAX derives automatically in the reference
+ * (interpax/_spline.py:581-589, 779-800, 1070-1099).  q / knots / perm are HOST arrays of ndim
+ * device pointers; grad_tables a HOST array of 2^ndim device pointers in the reference's
+ * stacking order (IPX_CUBIC) or of one pointer (IPX_LINEAR).  IPX_NEAREST: IPX_EUNSUPPORTED.
+ * Queries replaced by an extrapolation fill contribute nothing.
+ * --------------------------------------------------------------------------------- */
+int ipx_vjp_tables_f32(int32_t ndim, const float* const* q, int64_t nq, const float* const* knots,
+                       const int32_t* const* perm, const int32_t* n, int64_t batch,
+                       int32_t method_class, int32_t periodic_mask, const ipx_params* params,
+                       int32_t params_on_device, const float* cotangent, float* const* grad_tables,
+                       void* stream);
+int ipx_vjp_tables_f64(int32_t ndim, const double* const* q, int64_t nq, const double* const* knots,
+                       const int32_t* const* perm, const int32_t* n, int64_t batch,
+                       int32_t method_class, int32_t periodic_mask, const ipx_params* params,
+                       int32_t params_on_device, const double* cotangent, double* const* grad_tables,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,7 @@ from .api import (
     interp1d,
     interp2d,
     interp3d,
+    vjp_tables,
 )
 
 __all__ = [
@@ -30,6 +31,7 @@ __all__ = [
     "interp1d",
     "interp2d",
     "interp3d",
+    "vjp_tables",
 ]
 
 __version__ = "0.1.0"

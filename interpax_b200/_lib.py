@@ -61,7 +61,7 @@ SYMBOLS = (
     + [
         f"ipx_{name}_{t}"
         for name in ("bin_index", "slopes", "periodic_knots", "pad_periodic", "pack", "cell_order", "gather",
-                     "gather_multi", "scatter")
+                     "gather_multi", "scatter", "vjp_tables")
         for t in ("f32", "f64")
     ]
 )
@@ -120,6 +120,10 @@ def _declare(lib: C.CDLL) -> None:
         f.restype = C.c_int
         f.argtypes = [i32, C.POINTER(vp), i64, C.POINTER(vp), C.POINTER(i32), i32, C.POINTER(Params), i32,
                       vp, vp, vp]
+        f = getattr(lib, f"ipx_vjp_tables_{t}")
+        f.restype = C.c_int
+        f.argtypes = [i32, C.POINTER(vp), i64, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), i64, i32, i32,
+                      C.POINTER(Params), i32, vp, C.POINTER(vp), vp]
         f = getattr(lib, f"ipx_gather_multi_{t}")
         f.restype = C.c_int
         f.argtypes = [i32, C.POINTER(vp), vp, i64, C.POINTER(vp), vp]

@@ -674,6 +674,54 @@ def approx_df(x, f, method="cubic", axis=-1, **kwargs):
     return out if want_torch else out.cpu().numpy()
 
 
+def vjp_tables(qs, knots, fshape, cotangent, method="cubic", derivative=0, extrap=False, period=None):
+    """Reverse-mode rule of ``interp{1,2,3}d`` with respect to its tables.
+
+    ``qs`` / ``knots``: tuples of the query and knot arrays (1, 2 or 3 of each); ``fshape`` the
+    shape of ``f``; ``cotangent`` an array of the output's shape.  Returns a dict of gradients
+    with the shape of ``f``: ``{"f": ...}`` for ``method="linear"`` and ``{"f", "fx", ...}`` (the
+    reference's table names) for the cubic family, i.e. the transpose of the map
+    tables -> output that JAX derives by differentiating the gathers and the ``A @ F``
+    contraction (interpax/_spline.py:581-589, 779-800, 1070-1099).  The dependence of slope
+    tables on ``f`` (``approx_df``) is not included: this is the rule for the tables as inputs.
+    """
+    ndim = len(knots)
+    errorif(ndim not in (1, 2, 3) or len(qs) != ndim, ValueError, "need 1, 2 or 3 query and knot arrays")
+    errorif(method == "nearest", NotImplementedError, "nearest-neighbour selection has no table gradient")
+    errorif(method not in METHODS_1D, ValueError, f"unknown method {method}")
+    fshape = tuple(int(v) for v in fshape)
+    _check_shapes(ndim, knots, fshape)
+    io = _Inputs(qs, knots, cotangent)
+    errorif(io.complex, NotImplementedError, "complex cotangents: pass real and imaginary parts separately")
+    kn = [io.coords(k) for k in knots]
+    qd, qshape, _ = io.queries(qs)
+    qd = [q.to(io.dev) for q in qd]
+    batch = int(np.prod(fshape[ndim:], dtype=np.int64))
+    cot = _to_dev(cotangent, io.rdt, io.dev).reshape(-1)
+    errorif(cot.numel() != qd[0].numel() * batch, ValueError, "cotangent must have the shape of the output")
+    periods = _parse_ndarg(period, ndim)
+    derivs = _parse_ndarg(derivative, ndim)
+    ex = _parse_extrap(extrap, ndim)
+    mask = 0
+    perms = [None] * ndim
+    kuse = list(kn)
+    for ax in range(ndim):
+        if periods[ax] is not None:
+            kuse[ax], perms[ax] = _periodic_knots_dev(kn[ax], periods[ax])
+            mask |= L.IPX_PERIODIC(ax)
+    mclass = _method_class(method)
+    names = TABLES[ndim] if mclass == L.IPX_CUBIC else ("f",)
+    grads = [torch.zeros(fshape, dtype=io.tdt, device=io.dev) for _ in names]
+    params = _make_params(ndim, derivs, ex, periods)
+    lib = L.load()
+    fn = getattr(lib, f"ipx_vjp_tables_{_suffix(qd[0])}")
+    narr = (C.c_int32 * ndim)(*[int(fshape[ax]) for ax in range(ndim)])
+    L.check(fn(ndim, _ptr_array(qd), qd[0].numel(), _ptr_array(kuse), _ptr_array(perms), narr, batch, mclass,
+               mask, C.byref(params), 0, _ptr(cot), _ptr_array(grads), _stream()), "ipx_vjp_tables")
+    out = dict(zip(names, grads))
+    return out if io.want_torch else {k: v.cpu().numpy() for k, v in out.items()}
+
+
 def bin_index(x, q):
     """``clip(searchsorted(x, q, side="right"), 1, len(x)-1)`` on the device -- the interval
     lookup of _spline.py:571 on its own (int32)."""

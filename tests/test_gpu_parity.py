@@ -798,3 +798,46 @@ def test_more_than_2_to_31_queries():
     for lo in (0, 2**31 + 5, nq - 4096):
         want = ipx.interp1d(q32[lo:lo + 4096].clone(), x.to(torch.float32), f.to(torch.float32), "linear", 0, True)
         assert torch.equal(lin[lo:lo + 4096][:want.numel()], want)
+
+
+# ------------------------------------------------------------------ reverse mode w.r.t. the tables
+@pytest.mark.parametrize("ndim", [1, 2, 3])
+def test_vjp_tables_is_the_transpose_of_the_evaluation(ndim):
+    """<cot, eval(tables + dT) - eval(tables)> == sum_tables <grad, dT>: the evaluation is linear
+    in its tables (away from extrapolation fills), so the identity is exact up to rounding.
+    Checked for the cubic family (all 2^d tables) and linear, with periodic axes, fills,
+    derivatives and a batch, and against the oracle evaluating the perturbed tables."""
+    rng = np.random.default_rng(80 + ndim)
+    ns = [11, 9, 8][:ndim]
+    names = {1: ("f", "fx"), 2: ("f", "fx", "fy", "fxy"), 3: ("f", "fx", "fy", "fz", "fxy", "fxz", "fyz", "fxyz")}[ndim]
+    knots = [knots_nonuniform(rng, n, 0.0, 2.0, np.float64) for n in ns]
+    nq = 3000
+    qs = [rng.uniform(-0.2, 2.2, nq) for _ in range(ndim)]
+    ofun = (O.interp1d, O.interp2d, O.interp3d)[ndim - 1]
+    for batch_shape in ((), (2,)):
+        fshape = (*ns, *batch_shape)
+        for method, deriv, extrap, period in (("cubic", 0, True, None), ("cubic", 1, (True, 0.5), None),
+                                              ("cubic", 0, False, 2.3), ("linear", 0, False, None),
+                                              ("linear", 1, True, None)):
+            per = period if (ndim == 1 or period is None) else (period,) + (None,) * (ndim - 1)
+            tabs = {nm: rng.normal(size=fshape) for nm in names}
+            dtab = {nm: rng.normal(size=fshape) for nm in names}
+            cot = rng.normal(size=(nq, *batch_shape))
+            grads = ipx.vjp_tables(qs, knots, fshape, cot, method, deriv, extrap, per)
+            if method == "linear":
+                assert set(grads) == {"f"}
+                base = ofun(*qs, *knots, tabs["f"], method, deriv, extrap, per)
+                pert = ofun(*qs, *knots, tabs["f"] + dtab["f"], method, deriv, extrap, per)
+                rhs = float(np.sum(grads["f"] * dtab["f"]))
+            else:
+                assert set(grads) == set(names)
+                kw = {nm: tabs[nm] for nm in names[1:]}
+                kw2 = {nm: tabs[nm] + dtab[nm] for nm in names[1:]}
+                base = ofun(*qs, *knots, tabs["f"], method, deriv, extrap, per, **kw)
+                pert = ofun(*qs, *knots, tabs["f"] + dtab["f"], method, deriv, extrap, per, **kw2)
+                rhs = float(sum(np.sum(grads[nm] * dtab[nm]) for nm in names))
+            d = pert - base
+            d = np.where(np.isfinite(d), d, 0.0)  # NaN fills (extrap=False) carry no gradient
+            lhs = float(np.sum(cot * d))
+            scale = float(np.sum(np.abs(cot) * np.abs(d))) + 1e-300
+            assert abs(lhs - rhs) <= 1e-11 * scale, (method, deriv, extrap, per, lhs, rhs)
