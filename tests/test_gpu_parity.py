@@ -841,3 +841,39 @@ def test_vjp_tables_is_the_transpose_of_the_evaluation(ndim):
             lhs = float(np.sum(cot * d))
             scale = float(np.sum(np.abs(cot) * np.abs(d))) + 1e-300
             assert abs(lhs - rhs) <= 1e-11 * scale, (method, deriv, extrap, per, lhs, rhs)
+
+
+def test_full_size_properties_f32_3d():
+    """float32 tile kernel (three resident CTAs per SM, 32-byte records) on a 128^3 periodic
+    table with 2^22 queries: permutation invariance (bitwise), cell-sorted == random order,
+    presort == plain, oracle parity on a subsample."""
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(99)
+    n = 128
+    P = 2 * np.pi
+    x = (torch.arange(n, dtype=torch.float64, device=dev) * (P / n)).to(torch.float32)
+    z = torch.linspace(0, 1, n, dtype=torch.float32, device=dev)
+    f = torch.randn((n, n, n), dtype=torch.float32, device=dev, generator=g)
+    period = (P, P, None)
+    extrap = ((True, True), (True, True), (True, 0.0))
+    ip = ipx.Interpolator3D(x, x, z, f, "cubic", extrap, period)
+    nq = 1 << 22
+    q = [(torch.rand(nq, dtype=torch.float32, device=dev, generator=g) * 3 - 1) * P for _ in range(2)]
+    q.append(torch.rand(nq, dtype=torch.float32, device=dev, generator=g) * 1.1 - 0.05)
+    r = ip(*q)
+    assert r.dtype == torch.float32 and torch.isfinite(r).all()
+    perm = torch.randperm(nq, device=dev, generator=g)
+    assert torch.equal(ip(*[a[perm] for a in q]), r[perm])
+    h = P / n
+    key = ((torch.remainder(q[0], P) / h).floor().clamp(0, n - 1).long() * n
+           + (torch.remainder(q[1], P) / h).floor().clamp(0, n - 1).long()) * n + (q[2] * (n - 1)).floor().clamp(0, n - 2).long()
+    o = torch.argsort(key)
+    assert torch.equal(ip(*[a[o] for a in q]), r[o])          # tile path == direct path
+    assert torch.equal(ip(*q, presort=True), r)
+    m = 1 << 13
+    qn = [a[:m].cpu().numpy() for a in q]
+    xn, zn, fn = x.cpu().numpy(), z.cpu().numpy(), f.cpu().numpy()
+    want = O.Interpolator3D(xn, xn, zn, fn, "cubic", extrap, period)(*qn)
+    up = lambda v: v.astype(np.float64)
+    truth = O.Interpolator3D(up(xn), up(xn), up(zn), up(fn), "cubic", extrap, period)(*[up(v) for v in qn])
+    assert_parity(r[:m].cpu().numpy(), want, "f32 3-D", truth)
