@@ -197,6 +197,23 @@ int ipx_pack_f64(int32_t ndim, const double* const* tables, int64_t nodes_times_
                  double* out, void* stream);
 
 /* ---------------------------------------------------------------------------------
+ * Fused knot slopes + pack: the whole chain of Interpolator2D/3D.__init__
+ * (interpax/_spline.py:232-246, 380-393 -- fx, fy[, fz] from f; fxy from fx; fxz, fyz;
+ * fxyz from fxy) in ONE pass from f (C order, shape (n[0], .., n[ndim-1], batch)) to the
+ * IPX_AOS records, bit-identical to the per-table slopes followed by the pack above, but
+ * without materialising the 2^d - 1 intermediate tables.  knots / n are HOST arrays of ndim
+ * entries (device pointers / extents).  Three-point stencils only: IPX_SLOPE_CUBIC, _CARDINAL (opts->c), _MONOTONIC,
+ * _MONOTONIC0, ndim 2 or 3 and every n >= 3; anything else returns IPX_EUNSUPPORTED and the
+ * caller uses ipx_slopes_* + ipx_pack_*.
+ * --------------------------------------------------------------------------------- */
+int ipx_slopes_pack_f32(int32_t ndim, const float* const* knots, const int32_t* n, const float* f,
+                        int64_t batch, int32_t method, const ipx_slope_opts* opts, float* out,
+                        void* stream);
+int ipx_slopes_pack_f64(int32_t ndim, const double* const* knots, const int32_t* n,
+                        const double* f, int64_t batch, int32_t method, const ipx_slope_opts* opts,
+                        double* out, void* stream);
+
+/* ---------------------------------------------------------------------------------
  * Spatial pre-sort of the query stream (no counterpart in the reference, which evaluates
  * queries in the order given, interpax/_spline.py:1051-1099).
  * ipx_cell_order_*: order[k] = index of the k-th query in cell order (stable argsort of the

@@ -60,7 +60,7 @@ SYMBOLS = (
     + [f"ipx_eval{d}d_{t}" for d in (1, 2, 3) for t in ("f32", "f64")]
     + [
         f"ipx_{name}_{t}"
-        for name in ("bin_index", "slopes", "periodic_knots", "pad_periodic", "pack", "cell_order", "gather",
+        for name in ("bin_index", "slopes", "slopes_pack", "periodic_knots", "pad_periodic", "pack", "cell_order", "gather",
                      "gather_multi", "scatter", "vjp_tables")
         for t in ("f32", "f64")
     ]
@@ -116,6 +116,9 @@ def _declare(lib: C.CDLL) -> None:
         f = getattr(lib, f"ipx_pack_{t}")
         f.restype = C.c_int
         f.argtypes = [i32, C.POINTER(vp), i64, vp, vp]
+        f = getattr(lib, f"ipx_slopes_pack_{t}")
+        f.restype = C.c_int
+        f.argtypes = [i32, C.POINTER(vp), C.POINTER(i32), vp, i64, i32, C.POINTER(SlopeOpts), vp, vp]
         f = getattr(lib, f"ipx_cell_order_{t}")
         f.restype = C.c_int
         f.argtypes = [i32, C.POINTER(vp), i64, C.POINTER(vp), C.POINTER(i32), i32, C.POINTER(Params), i32,

@@ -576,6 +576,7 @@ def _interp(ndim, qs, knots, f, method, derivative, extrap, period, kwargs, retu
     mask = 0
     perms = [None] * ndim
     kuse = list(kn)
+    packed = None
     if mclass == L.IPX_CUBIC:
         missing = [n for n in names[1:] if tabs[n] is None]
         if missing and any(p is not None for p in pk):
@@ -594,13 +595,17 @@ def _interp(ndim, qs, knots, f, method, derivative, extrap, period, kwargs, retu
                 if pk[ax] is not None:
                     kuse[ax], perms[ax] = pk[ax]
                     mask |= L.IPX_PERIODIC(ax)
-        for name, src, ax in CHAIN[ndim]:
-            if tabs[name] is None:
-                tabs[name] = _slopes_dev(kuse[ax], tabs[src], method, ax, kwargs)
-        for n in names[1:]:
-            errorif(tabs[n].shape != tabs["f"].shape, ValueError,
-                    f"{n} must have the same shape as f")
-        tables = [tabs[n] for n in names]
+        if len(missing) == len(names) - 1:
+            # no slope table supplied: f (padded where periodic) -> records in one launch
+            packed = _slopes_pack_dev(ndim, kuse, tabs["f"], batch, method, kwargs)
+        if packed is None:
+            for name, src, ax in CHAIN[ndim]:
+                if tabs[name] is None:
+                    tabs[name] = _slopes_dev(kuse[ax], tabs[src], method, ax, kwargs)
+            for n in names[1:]:
+                errorif(tabs[n].shape != tabs["f"].shape, ValueError,
+                        f"{n} must have the same shape as f")
+            tables = [tabs[n] for n in names]
     else:
         for ax in range(ndim):
             if pk[ax] is not None:
@@ -616,7 +621,9 @@ def _interp(ndim, qs, knots, f, method, derivative, extrap, period, kwargs, retu
     # separate tables in place.
     layout = L.IPX_SOA
     nq_total = int(np.prod([int(v) for v in np.broadcast_shapes(*[_shape(q) for q in qs])], dtype=np.int64))
-    if mclass == L.IPX_CUBIC and batch == 1 and nq_total >= (1 << 16) and 2 * nq_total >= tables[0].numel():
+    if mclass == L.IPX_CUBIC and packed is not None:
+        tables, layout = [packed], L.IPX_AOS
+    elif mclass == L.IPX_CUBIC and batch == 1 and nq_total >= (1 << 16) and 2 * nq_total >= tables[0].numel():
         tables, layout = [_pack_dev(ndim, tables)], L.IPX_AOS
 
     def launch(dq, dout, want_idx):
@@ -740,6 +747,52 @@ def bin_index(x, q):
 
 
 # --------------------------------------------------------------------------- containers
+# table name -> slot in the packed record, keyed by the record length (last axis fastest)
+_RECORD_SLOT = {
+    2: {"f": 0, "fx": 1},
+    4: {"f": 0, "fy": 1, "fx": 2, "fxy": 3},
+    8: {"f": 0, "fz": 1, "fy": 2, "fyz": 3, "fx": 4, "fxz": 5, "fxy": 6, "fxyz": 7},
+}
+_FUSED_SLOPES = ("cubic", "cardinal", "catmull-rom", "monotonic", "monotonic-0")
+
+
+def _slopes_pack_dev(ndim, kn, f, batch, method, kwargs):
+    """f -> IPX_AOS records in one launch (ipx_slopes_pack_*), or None where the C ABI says
+    IPX_EUNSUPPORTED (1-D, cubic2 / akima, an axis shorter than 3 knots)."""
+    if ndim < 2 or method not in _FUSED_SLOPES or any(int(f.shape[ax]) < 3 for ax in range(ndim)):
+        return None
+    lib = L.load()
+    opts = L.SlopeOpts()
+    opts.c = float(kwargs.get("c", 0)) if method == "cardinal" else 0.0
+    out = torch.empty(tuple(f.shape) + (1 << ndim,), dtype=f.dtype, device=f.device)
+    narr = (C.c_int32 * ndim)(*[int(f.shape[ax]) for ax in range(ndim)])
+    fn = getattr(lib, f"ipx_slopes_pack_{_suffix(f)}")
+    rc = fn(ndim, _ptr_array(list(kn)), narr, _ptr(f), batch, _SLOPE_CODE[method], C.byref(opts), _ptr(out),
+            _stream())
+    if rc == L.IPX_EUNSUPPORTED:
+        return None
+    L.check(rc, "ipx_slopes_pack")
+    return out
+
+
+class _RecordTables:
+    """The 2^d tables of an interpolator whose records were built in one pass: `f` is the
+    caller's array; a slope table is split off the packed records (a strided device copy)
+    the first time it is read and kept."""
+
+    def __init__(self, names, f, packed):
+        self._names = names
+        self._packed = packed
+        self._have = {"f": f}
+
+    def __getitem__(self, name):
+        if name not in self._have:
+            f = self._have["f"]
+            slot = _RECORD_SLOT[len(self._names)][name]
+            self._have[name] = self._packed.view(*f.shape, len(self._names))[..., slot].contiguous()
+        return self._have[name]
+
+
 class _InterpolatorND:
     """Shared machinery of Interpolator1D/2D/3D (_spline.py:48-441): tables live on the
     device; slopes are precomputed once on the UN-padded tables (:380-393) and, for the
@@ -769,17 +822,24 @@ class _InterpolatorND:
         self._fshape = fshape
         self._knots = kn
         tabs = {"f": io.table(f)}
+        self._batch = int(np.prod(tabs["f"].shape[ndim:], dtype=np.int64))
+        self._pk_cache = {}
+        self._packed = None
+        if all(v is None for v in given.values()):
+            # nothing supplied: one fused pass f -> packed records; the separate slope tables
+            # (`.derivs`) are split off the records only if somebody asks for them
+            self._packed = _slopes_pack_dev(ndim, kn, tabs["f"], self._batch, method, kwargs)
+        if self._packed is not None:
+            self._tabs = _RecordTables(names, tabs["f"], self._packed)
+            return
         for n in names[1:]:
             tabs[n] = None if given[n] is None else io.table(given[n])
         for name, src, ax in CHAIN[ndim]:
             if tabs[name] is None:
                 tabs[name] = _slopes_dev(kn[ax], tabs[src], method, ax, kwargs)
         self._tabs = tabs
-        self._batch = int(np.prod(tabs["f"].shape[ndim:], dtype=np.int64))
-        self._packed = None
         if _method_class(method) == L.IPX_CUBIC:
             self._packed = _pack_dev(ndim, [tabs[n] for n in names])
-        self._pk_cache = {}
 
     # the reference exposes these as pytree leaves
     @property

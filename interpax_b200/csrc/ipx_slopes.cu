@@ -25,8 +25,10 @@ template <typename T> struct SlopeArgs {
 template <typename T>
 __device__ __forceinline__ T secant(const SlopeArgs<T>& a, int64_t base, int k) {
   // s_k = (f[k+1] - f[k]) * where(dx == 0, 0, 1/dx)
+  // products and sums through mul_rn / add_rn so that no caller contracts them into an FMA:
+  // the per-table kernels and the fused one-pass kernel below must produce the same bits
   T df = a.f[base + (int64_t)(k + 1) * a.inner] - a.f[base + (int64_t)k * a.inner];
-  return safe_recip(a.x[k + 1] - a.x[k]) * df;
+  return mul_rn(safe_recip(a.x[k + 1] - a.x[k]), df);
 }
 
 template <typename T> __device__ __forceinline__ T sign_of(T v) {
@@ -59,7 +61,7 @@ template <typename T> __global__ void slopes_cubic_kernel(const SlopeArgs<T> a) 
     T v;
     if (k == 0) v = secant(a, base, 0);
     else if (k == a.n - 1) v = secant(a, base, a.n - 2);
-    else v = T(0.5) * (secant(a, base, k - 1) + secant(a, base, k));
+    else v = T(0.5) * add_rn(secant(a, base, k - 1), secant(a, base, k));
     a.out[e] = v;
   }
 }
@@ -84,7 +86,7 @@ template <typename T> __global__ void slopes_cardinal_kernel(const SlopeArgs<T> 
 template <typename T>
 __device__ __forceinline__ T pchip_edge(T h0, T h1, T m0, T m1) {
   // _fd_derivs.py:365-376
-  T d = ((T(2) * h0 + h1) * m0 - h0 * m1) / (h0 + h1);
+  T d = add_rn(mul_rn(T(2) * h0 + h1, m0), -mul_rn(h0, m1)) / (h0 + h1);
   bool mask = sign_of(d) != sign_of(m0);
   bool mask2 = (sign_of(m0) != sign_of(m1)) && (t_abs(d) > T(3) * t_abs(m0));
   bool mmm = (!mask) && mask2;
@@ -564,7 +566,397 @@ static int launch_slopes(const T* x, int32_t n, const T* f, int64_t outer, int64
   return cudaPeekAtLastError() == cudaSuccess ? IPX_OK : IPX_ELAUNCH;
 }
 
+// ------------------------------------------------------------------ fused slopes + pack
+// One pass from f to the packed records the evaluation streams: every chain table of
+// Interpolator2D/3D.__init__ (_spline.py:232-246, 380-393: fx, fy, fz from f; fxy from fx;
+// fxz, fyz from fx, fy; fxyz from fxy) for the three-point stencils, without materialising
+// the 2^d - 1 intermediate tables.  A warp owns a span of the last axis (one knot per lane,
+// neighbours by shuffle) and marches along the axis before it with a rolling three-row
+// window in registers, applying the same stencil arithmetic as the per-table kernels above,
+// so the packed array is bit-identical to pack(slopes chain).  Interval widths and their
+// reciprocals are computed once per CTA into shared memory.
+//
+// Window of an axis with n >= 3 knots: the three consecutive knots ws, ws+1, ws+2 with
+// ws = clamp(k-1, 0, n-3); p = k - ws is 1 in the interior, 0 / 2 at the first / last knot,
+// where the one-sided forms use knots (0, 1, 2) / (n-3, n-2, n-1).
+constexpr int kFusedKnotCap = 6144;  // sum of the axis lengths that fits the shared tables
+
+template <typename T> struct AxisWin {
+  T h01, h12, r01, r12, r02;
+  int p;
+};
+
+// sh: widths h[0..n-2] then reciprocals r[0..n-2] of this axis
+template <typename T, int METHOD>
+__device__ __forceinline__ AxisWin<T> axis_window(const T* __restrict__ x, const T* sh, int n,
+                                                  int k, int& ws) {
+  ws = min(max(k - 1, 0), n - 3);
+  AxisWin<T> w;
+  w.h01 = sh[ws];
+  w.h12 = sh[ws + 1];
+  w.r01 = sh[n - 1 + ws];
+  w.r12 = sh[n + ws];
+  w.r02 = T(0);
+  if constexpr (METHOD == IPX_SLOPE_CARDINAL) w.r02 = safe_recip(__ldg(x + ws + 2) - __ldg(x + ws));
+  w.p = k - ws;
+  return w;
+}
+
+template <typename T> __device__ __forceinline__ T sel3(int p, T a0, T a1, T a2) {
+  return p == 0 ? a0 : (p == 1 ? a1 : a2);
+}
+
+template <typename T, int METHOD>
+__device__ __forceinline__ T stencil3(const AxisWin<T>& w, T g0, T g1, T g2, T one_minus_c) {
+  if constexpr (METHOD == IPX_SLOPE_CUBIC) {
+    T s01 = mul_rn(w.r01, g1 - g0), s12 = mul_rn(w.r12, g2 - g1);
+    return w.p == 0 ? s01 : (w.p == 2 ? s12 : T(0.5) * add_rn(s01, s12));
+  } else if constexpr (METHOD == IPX_SLOPE_CARDINAL) {
+    T v = w.p == 0 ? (g1 - g0) * w.r01 : (w.p == 2 ? (g2 - g1) * w.r12 : w.r02 * (g2 - g0));
+    return one_minus_c * v;
+  } else {
+    T s01 = mul_rn(w.r01, g1 - g0), s12 = mul_rn(w.r12, g2 - g1);
+    if (w.p != 1) {
+      if constexpr (METHOD == IPX_SLOPE_MONOTONIC0) return T(0);
+      T hi0 = w.p == 0 ? w.r01 : w.r12, hi1 = w.p == 0 ? w.r12 : w.r01;
+      T m0 = w.p == 0 ? s01 : s12, m1 = w.p == 0 ? s12 : s01;
+      return pchip_edge(T(1) / hi0, T(1) / hi1, m0, m1);
+    }
+    T h0 = w.h01, h1 = w.h12, m0 = s01, m1 = s12;
+    bool cond = (sign_of(m1) != sign_of(m0)) || (m1 == T(0)) || (m0 == T(0));
+    T w1 = T(2) * h1 + h0;
+    T w2 = h1 + T(2) * h0;
+    T whmean = safediv(safediv(w1, m0) + safediv(w2, m1), w1 + w2);
+    return cond ? T(0) : safediv(T(1), whmean);
+  }
+}
+
+// The same stencils in centred form, for the axis that runs across the lanes of a warp:
+// g0 is this lane's value at knot k, its neighbours k-1 / k+1 come from the adjacent lanes.
+// h / r: widths and reciprocal widths of this axis in shared memory.  Must be called by all
+// 32 lanes (shuffles); the result is meaningful on lanes whose neighbours hold k-1 and k+1.
+template <typename T, int METHOD>
+__device__ __forceinline__ T stencil_lanes(const T* __restrict__ x, const T* h, const T* r, int n,
+                                           int k, T g0, T one_minus_c) {
+  const unsigned full = 0xffffffffu;
+  const T gm = __shfl_up_sync(full, g0, 1), gp = __shfl_down_sync(full, g0, 1);
+  const int km = min(max(k - 1, 0), n - 2), kp = min(max(k, 0), n - 2);
+  const bool first = k <= 0, last = k >= n - 1;
+  if constexpr (METHOD == IPX_SLOPE_CARDINAL) {
+    const int lo = max(k - 1, 0), hi = min(k + 1, n - 1);
+    T r2 = safe_recip(__ldg(x + hi) - __ldg(x + lo));
+    T v = first ? (gp - g0) * r[kp] : (last ? (g0 - gm) * r[km] : r2 * (gp - gm));
+    return one_minus_c * v;
+  } else {
+    const T sm = mul_rn(r[km], g0 - gm), sp = mul_rn(r[kp], gp - g0);
+    if constexpr (METHOD == IPX_SLOPE_CUBIC) {
+      return first ? sp : (last ? sm : T(0.5) * add_rn(sm, sp));
+    } else {
+      T edge = T(0);
+      if constexpr (METHOD == IPX_SLOPE_MONOTONIC) {
+        // one-sided ends use the next / previous secant as well (_fd_derivs.py:365-386)
+        const T sp_next = __shfl_down_sync(full, sp, 1), sm_prev = __shfl_up_sync(full, sm, 1);
+        if (first || last) {
+          T hi0 = first ? r[kp] : r[km];
+          T hi1 = first ? r[min(kp + 1, n - 2)] : r[max(km - 1, 0)];
+          edge = pchip_edge(T(1) / hi0, T(1) / hi1, first ? sp : sm, first ? sp_next : sm_prev);
+        }
+      }
+      if (first || last) return edge;
+      T h0 = h[km], h1 = h[kp], m0 = sm, m1 = sp;
+      bool cond = (sign_of(m1) != sign_of(m0)) || (m1 == T(0)) || (m0 == T(0));
+      T w1 = T(2) * h1 + h0;
+      T w2 = h1 + T(2) * h0;
+      T whmean = safediv(safediv(w1, m0) + safediv(w2, m1), w1 + w2);
+      return cond ? T(0) : safediv(T(1), whmean);
+    }
+  }
+}
+
+template <typename T> struct FusedArgs {
+  const T* __restrict__ x[3];
+  const T* __restrict__ f;
+  T* __restrict__ out;
+  int32_t batch;
+  int32_t n[3];
+  int32_t wide;  // out is 32-byte aligned: 256-bit stores
+  T one_minus_c;
+};
+
+// one record: 2^d values, 16-byte aligned at least
+__device__ __forceinline__ void store_record4(double* o, bool wide, double a, double b, double c, double d) {
+  if (wide) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(o), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+  } else {
+    *reinterpret_cast<double2*>(o) = make_double2(a, b);
+    *reinterpret_cast<double2*>(o + 2) = make_double2(c, d);
+  }
+}
+__device__ __forceinline__ void store_record4(float* o, bool, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(o) = make_float4(a, b, c, d);
+}
+__device__ __forceinline__ void store_record8(double* o, bool wide, const double (&v)[8]) {
+  store_record4(o, wide, v[0], v[1], v[2], v[3]);
+  store_record4(o + 4, wide, v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store_record8(float* o, bool wide, const float (&v)[8]) {
+  if (wide) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o), "f"(v[0]), "f"(v[1]),
+                 "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+  } else {
+    *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+// widths and reciprocal widths of every axis into shared memory; returns per-axis offsets
+template <typename T, int ND>
+__device__ __forceinline__ void stage_widths(const FusedArgs<T>& a, T* sh, int* off) {
+  int o = 0;
+#pragma unroll
+  for (int ax = 0; ax < ND; ++ax) {
+    off[ax] = o;
+    const int n = a.n[ax];
+    for (int k = threadIdx.x; k < n - 1; k += blockDim.x) {
+      T h = __ldg(a.x[ax] + k + 1) - __ldg(a.x[ax] + k);
+      sh[o + k] = h;
+      sh[o + n - 1 + k] = safe_recip(h);
+    }
+    o += 2 * (n - 1);
+  }
+  __syncthreads();
+}
+
+// A warp covers kLaneSpan consecutive knots of the last axis plus one halo knot on each side
+// (lane 0 and lane 31), so every neighbour a centred stencil needs is one shuffle away.  The
+// last chunk of a row is shifted back to end at the last knot (its overlap with the previous
+// chunk rewrites the same values), which keeps both one-sided ends at least two lanes inside.
+constexpr int kLaneSpan = 30;
+
+// window of knot k from the shared width table of an axis, given its first knot ws
+template <typename T, int METHOD>
+__device__ __forceinline__ AxisWin<T> window_at(const T* __restrict__ x, const T* sh, int n, int k,
+                                                int ws) {
+  AxisWin<T> w;
+  w.h01 = sh[ws];
+  w.h12 = sh[ws + 1];
+  w.r01 = sh[n - 1 + ws];
+  w.r12 = sh[n + ws];
+  w.r02 = T(0);
+  if constexpr (METHOD == IPX_SLOPE_CARDINAL) w.r02 = safe_recip(__ldg(x + ws + 2) - __ldg(x + ws));
+  w.p = k - ws;
+  return w;
+}
+
+constexpr int kRowSpan = 32;  // rows a warp marches over with its rolling window
+
+// 2-D: a warp owns kLaneSpan knots of y (lanes) and marches over kRowSpan consecutive x rows,
+// keeping the three-row x window of f in registers: per node 1 load, 1 x stencil, 2 y stencils.
+template <typename T, int METHOD>
+__global__ void __launch_bounds__(kSlopeThreads) slopes_pack2d_kernel(const FusedArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char fused_smem[];
+  T* sh = reinterpret_cast<T*>(fused_smem);
+  int off[2];
+  stage_widths<T, 2>(a, sh, off);
+  const int nx = a.n[0], ny = a.n[1], B = a.batch;
+  const int lane = threadIdx.x & 31;
+  const int64_t inner = (int64_t)ny * B;
+  const T omc = a.one_minus_c;
+  const bool wide = a.wide != 0;
+  const T* hy = sh + off[1];
+  const T* ry = hy + (ny - 1);
+  const unsigned chunks = (ny + kLaneSpan - 1) / kLaneSpan;
+  const unsigned xsegs = (nx + kRowSpan - 1) / kRowSpan;
+  const unsigned items = chunks * xsegs;
+  const unsigned warps = gridDim.x * (blockDim.x >> 5);
+  for (unsigned item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); item < items;
+       item += warps) {
+    const int xs = (int)(item / chunks), ch = (int)(item - (unsigned)xs * chunks);
+    const int jbase = min(ch * kLaneSpan, max(ny - kLaneSpan, 0));
+    const int j = jbase - 1 + lane, jc = min(max(j, 0), ny - 1);
+    const bool valid = lane >= 1 && lane <= kLaneSpan && j < ny;
+    const int ibeg = xs * kRowSpan, iend = min(nx, ibeg + kRowSpan);
+    for (int b = 0; b < B; ++b) {
+      const T* col = a.f + (int64_t)jc * B + b;  // (0, jc, b)
+      T* orow = a.out + ((int64_t)ibeg * inner + (int64_t)jc * B + b) * 4;
+      int ws = min(max(ibeg - 1, 0), nx - 3);
+      T v0 = __ldg(col + (int64_t)ws * inner), v1 = __ldg(col + (int64_t)(ws + 1) * inner),
+        v2 = __ldg(col + (int64_t)(ws + 2) * inner);
+      T pv = __ldg(col + (int64_t)min(ws + 3, nx - 1) * inner);  // enters at the next shift
+      for (int i = ibeg; i < iend; ++i) {
+        const int wsn = min(max(i - 1, 0), nx - 3);
+        if (wsn != ws) {  // warp-uniform
+          ws = wsn;
+          v0 = v1; v1 = v2; v2 = pv;
+          pv = __ldg(col + (int64_t)min(ws + 3, nx - 1) * inner);
+        }
+        const AxisWin<T> wx = window_at<T, METHOD>(a.x[0], sh + off[0], nx, i, ws);
+        const T fx = stencil3<T, METHOD>(wx, v0, v1, v2, omc);
+        const T f0 = sel3(wx.p, v0, v1, v2);
+        const T fy = stencil_lanes<T, METHOD>(a.x[1], hy, ry, ny, j, f0, omc);
+        const T fxy = stencil_lanes<T, METHOD>(a.x[1], hy, ry, ny, j, fx, omc);
+        if (valid) store_record4(orow, wide, f0, fy, fx, fxy);
+        orow += inner * 4;
+      }
+    }
+  }
+}
+
+// 3-D: a warp owns kLaneSpan knots of z (lanes) and marches over kRowSpan consecutive y rows
+// of one x plane, keeping the three-row y window of (f, fx) in registers: per node 3 loads
+// (the x window of the row that enters), 1 x stencil, 2 y stencils, 4 z stencils.
+template <typename T, int METHOD>
+__global__ void __launch_bounds__(kSlopeThreads, 3) slopes_pack3d_kernel(const FusedArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char fused_smem[];
+  T* sh = reinterpret_cast<T*>(fused_smem);
+  int off[3];
+  stage_widths<T, 3>(a, sh, off);
+  const int nx = a.n[0], ny = a.n[1], nz = a.n[2], B = a.batch;
+  const int lane = threadIdx.x & 31;
+  const int64_t sy = (int64_t)nz * B, sx = (int64_t)ny * sy;
+  const T omc = a.one_minus_c;
+  const bool wide = a.wide != 0;
+  const T* hz = sh + off[2];
+  const T* rz = hz + (nz - 1);
+  const unsigned chunks = (nz + kLaneSpan - 1) / kLaneSpan;
+  const unsigned ysegs = (ny + kRowSpan - 1) / kRowSpan;
+  const unsigned per_plane = chunks * ysegs;
+  const unsigned items = (unsigned)nx * per_plane;
+  const unsigned warps = gridDim.x * (blockDim.x >> 5);
+  for (unsigned item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); item < items;
+       item += warps) {
+    const int i = (int)(item / per_plane);
+    const unsigned rem = item - (unsigned)i * per_plane;
+    const int ys = (int)(rem / chunks), ch = (int)(rem - (unsigned)ys * chunks);
+    const int kbase = min(ch * kLaneSpan, max(nz - kLaneSpan, 0));
+    const int k = kbase - 1 + lane, kc = min(max(k, 0), nz - 1);
+    const bool valid = lane >= 1 && lane <= kLaneSpan && k < nz;
+    const int jbeg = ys * kRowSpan, jend = min(ny, jbeg + kRowSpan);
+    int i0;
+    const AxisWin<T> wx = axis_window<T, METHOD>(a.x[0], sh + off[0], nx, i, i0);
+    for (int b = 0; b < B; ++b) {
+      const T* plane = a.f + (int64_t)i0 * sx + (int64_t)kc * B + b;  // (i0, 0, kc, b)
+      T* orow = a.out + ((((int64_t)i * ny + jbeg) * nz + kc) * B + b) * 8;
+      int ws = min(max(jbeg - 1, 0), ny - 3);
+      T gx[3], fr[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const T* col = plane + (int64_t)(ws + c) * sy;
+        T v0 = __ldg(col), v1 = __ldg(col + sx), v2 = __ldg(col + 2 * sx);
+        gx[c] = stencil3<T, METHOD>(wx, v0, v1, v2, omc);  // fx at (i, ws + c, k)
+        fr[c] = sel3(wx.p, v0, v1, v2);                    // f  at (i, ws + c, k)
+      }
+      // raw x window of the row that enters at the next shift, loaded one step ahead
+      const T* ncol = plane + (int64_t)min(ws + 3, ny - 1) * sy;
+      T p0 = __ldg(ncol), p1 = __ldg(ncol + sx), p2 = __ldg(ncol + 2 * sx);
+      for (int j = jbeg; j < jend; ++j) {
+        const int wsn = min(max(j - 1, 0), ny - 3);
+        if (wsn != ws) {  // warp-uniform
+          ws = wsn;
+          gx[0] = gx[1]; gx[1] = gx[2];
+          fr[0] = fr[1]; fr[1] = fr[2];
+          gx[2] = stencil3<T, METHOD>(wx, p0, p1, p2, omc);
+          fr[2] = sel3(wx.p, p0, p1, p2);
+          ncol = plane + (int64_t)min(ws + 3, ny - 1) * sy;
+          p0 = __ldg(ncol); p1 = __ldg(ncol + sx); p2 = __ldg(ncol + 2 * sx);
+        }
+        const AxisWin<T> wy = window_at<T, METHOD>(a.x[1], sh + off[1], ny, j, ws);
+        T rec[8];  // record order: last axis fastest
+        rec[0] = sel3(wy.p, fr[0], fr[1], fr[2]);
+        rec[4] = sel3(wy.p, gx[0], gx[1], gx[2]);
+        rec[2] = stencil3<T, METHOD>(wy, fr[0], fr[1], fr[2], omc);
+        rec[6] = stencil3<T, METHOD>(wy, gx[0], gx[1], gx[2], omc);
+#pragma unroll
+        for (int m = 0; m < 8; m += 2)
+          rec[m + 1] = stencil_lanes<T, METHOD>(a.x[2], hz, rz, nz, k, rec[m], omc);
+        if (valid) store_record8(orow, wide, rec);
+        orow += sy * 8;
+      }
+    }
+  }
+}
+
+template <typename T, int METHOD>
+static int launch_slopes_pack_m(int32_t ndim, const FusedArgs<T>& a, cudaStream_t s) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess)
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  size_t smem = 0;
+  for (int ax = 0; ax < ndim; ++ax) smem += 2 * (size_t)(a.n[ax] - 1) * sizeof(T);
+  const int64_t chunks = (a.n[ndim - 1] + kLaneSpan - 1) / kLaneSpan;
+  const int64_t items = ndim == 2 ? chunks * ((a.n[0] + kRowSpan - 1) / kRowSpan)
+                                  : (int64_t)a.n[0] * chunks * ((a.n[1] + kRowSpan - 1) / kRowSpan);
+  if (items > INT32_MAX) return IPX_EUNSUPPORTED;
+  const int64_t need = (items + kSlopeThreads / 32 - 1) / (kSlopeThreads / 32);
+  const int64_t cap = (int64_t)sms * 8;
+  const int grid = (int)(need < cap ? need : cap);
+  if (ndim == 2) {
+    auto k = slopes_pack2d_kernel<T, METHOD>;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return IPX_ELAUNCH;
+    k<<<grid, kSlopeThreads, smem, s>>>(a);
+  } else {
+    auto k = slopes_pack3d_kernel<T, METHOD>;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return IPX_ELAUNCH;
+    k<<<grid, kSlopeThreads, smem, s>>>(a);
+  }
+  return cudaPeekAtLastError() == cudaSuccess ? IPX_OK : IPX_ELAUNCH;
+}
+
+template <typename T>
+static int launch_slopes_pack(int32_t ndim, const T* const* knots, const int32_t* n, const T* f,
+                              int64_t batch, int32_t method, const ipx_slope_opts* opts, T* out,
+                              void* stream) {
+  if (knots == nullptr || n == nullptr || batch < 0) return IPX_EINVAL;
+  if (ndim < 1 || ndim > 3) return IPX_EINVAL;
+  if (ndim == 1) return IPX_EUNSUPPORTED;  // two tables: slopes + pack is already one pass each
+  if (method != IPX_SLOPE_CUBIC && method != IPX_SLOPE_CARDINAL && method != IPX_SLOPE_MONOTONIC &&
+      method != IPX_SLOPE_MONOTONIC0)
+    return (method >= 0 && method <= IPX_SLOPE_ZERO) ? IPX_EUNSUPPORTED : IPX_EINVAL;
+  FusedArgs<T> a{};
+  int64_t total = batch, knots_total = 0;
+  for (int ax = 0; ax < ndim; ++ax) {
+    if (knots[ax] == nullptr || n[ax] < 1) return IPX_EINVAL;
+    if (n[ax] < 3) return IPX_EUNSUPPORTED;  // the three-knot window needs n >= 3
+    a.x[ax] = knots[ax];
+    a.n[ax] = n[ax];
+    total *= n[ax];
+    knots_total += n[ax];
+  }
+  if (knots_total > kFusedKnotCap || batch > (1 << 20)) return IPX_EUNSUPPORTED;
+  if (ndim == 3 && (int64_t)n[0] * n[1] > INT32_MAX) return IPX_EUNSUPPORTED;
+  if (total == 0) return IPX_OK;
+  if (f == nullptr || out == nullptr) return IPX_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(out) & (2 * sizeof(T) - 1)) != 0) return IPX_EINVAL;
+  a.f = f;
+  a.out = out;
+  a.batch = (int32_t)batch;
+  a.wide = (reinterpret_cast<uintptr_t>(out) & 31) == 0;
+  a.one_minus_c = T(1) - (opts != nullptr ? T(opts->c) : T(0));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (method) {
+    case IPX_SLOPE_CUBIC: return launch_slopes_pack_m<T, IPX_SLOPE_CUBIC>(ndim, a, s);
+    case IPX_SLOPE_CARDINAL: return launch_slopes_pack_m<T, IPX_SLOPE_CARDINAL>(ndim, a, s);
+    case IPX_SLOPE_MONOTONIC: return launch_slopes_pack_m<T, IPX_SLOPE_MONOTONIC>(ndim, a, s);
+    default: return launch_slopes_pack_m<T, IPX_SLOPE_MONOTONIC0>(ndim, a, s);
+  }
+}
+
 }  // namespace ipx
+
+extern "C" int ipx_slopes_pack_f32(int32_t ndim, const float* const* knots, const int32_t* n,
+                                   const float* f, int64_t batch, int32_t method,
+                                   const ipx_slope_opts* opts, float* out, void* stream) {
+  return ipx::launch_slopes_pack<float>(ndim, knots, n, f, batch, method, opts, out, stream);
+}
+extern "C" int ipx_slopes_pack_f64(int32_t ndim, const double* const* knots, const int32_t* n,
+                                   const double* f, int64_t batch, int32_t method,
+                                   const ipx_slope_opts* opts, double* out, void* stream) {
+  return ipx::launch_slopes_pack<double>(ndim, knots, n, f, batch, method, opts, out, stream);
+}
 
 extern "C" size_t ipx_slopes_workspace_bytes(int32_t method, int32_t n, int32_t elem_size) {
   if (method == IPX_SLOPE_AKIMA) return 16;

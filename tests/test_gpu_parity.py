@@ -151,6 +151,75 @@ def test_slopes_duplicate_knots_and_flat_data(dtype):
         assert_parity(ipx.approx_df(xx, z, method, 0), O.approx_df(xx, z, method, 0).astype(dtype), method)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("method", ["cubic", "cardinal", "catmull-rom", "monotonic", "monotonic-0"])
+def test_fused_slopes_pack_is_bitwise_the_table_chain(method, dtype):
+    """ipx_slopes_pack_* (one pass f -> records) against the per-table chain
+    fx, fy, fz <- f; fxy <- fx; fxz, fyz; fxyz <- fxy followed by ipx_pack_*: same bits, also at
+    the one-sided ends, with duplicate knots, flat stretches and a trailing batch."""
+    rng = np.random.default_rng(41)
+    kw = {"c": 0.3} if method == "cardinal" else {}
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    for shape, batch in [((3, 3), ()), ((17, 9), ()), ((6, 5), (3,)), ((3, 3, 3), ()), ((9, 4, 13), ()),
+                         ((5, 6, 7), (2,)), ((33, 18, 21), ())]:
+        ndim = len(shape)
+        kn = [knots_nonuniform(rng, n, 0, 2, dtype) for n in shape]
+        if shape[0] > 8:
+            kn[0][4] = kn[0][5]  # a zero-width interval
+        f = rng.normal(size=shape + batch).astype(dtype)
+        if shape[-1] > 8:
+            f[..., 2:6] = f[..., 2:3]  # flat stretch along the last axis
+        kd = [torch.as_tensor(k, device="cuda") for k in kn]
+        fd = torch.as_tensor(f, device="cuda")
+        nb = int(np.prod(batch, dtype=np.int64))
+        got = api._slopes_pack_dev(ndim, kd, fd, nb, method, kw)
+        assert got is not None and got.dtype == tdt
+        tabs = {"f": fd}
+        for name, src, ax in api.CHAIN[ndim]:
+            tabs[name] = api._slopes_dev(kd[ax], tabs[src], method, ax, kw)
+        want = api._pack_dev(ndim, [tabs[n] for n in api.TABLES[ndim]])
+        g, w = got.cpu().numpy(), want.cpu().numpy()
+        assert np.array_equal(g.view(np.uint8), w.view(np.uint8)), (method, shape, batch)
+        # the class builds from the fused records and splits `.derivs` off them on demand
+        cls = ipx.Interpolator2D if ndim == 2 else ipx.Interpolator3D
+        obj = cls(*kd, fd, method=method, **kw)
+        assert isinstance(obj._tabs, api._RecordTables)
+        for name in api.TABLES[ndim][1:]:
+            assert torch.equal(obj.derivs[name], tabs[name]), (method, shape, name)
+        ref = (O.Interpolator2D if ndim == 2 else O.Interpolator3D)(*kn, f, method=method, **kw)
+        q = [rng.uniform(-0.1, 2.1, 500).astype(dtype) for _ in range(ndim)]
+        truth = None
+        if dtype == np.float32:
+            truth = (O.Interpolator2D if ndim == 2 else O.Interpolator3D)(
+                *[k.astype(np.float64) for k in kn], f.astype(np.float64), method=method, **kw)(
+                *[v.astype(np.float64) for v in q])
+        assert_parity(obj(*[torch.as_tensor(v, device="cuda") for v in q]).cpu().numpy(), ref(*q),
+                      f"{method} {shape}", truth)
+
+
+def test_fused_slopes_pack_unsupported_cases_use_the_table_chain():
+    rng = np.random.default_rng(42)
+    x, y = np.linspace(0, 1, 2), np.linspace(0, 1, 7)
+    f = rng.normal(size=(2, 7))
+    obj = ipx.Interpolator2D(x, y, f, method="cubic")          # an axis with two knots
+    assert not isinstance(obj._tabs, api._RecordTables)
+    obj = ipx.Interpolator2D(y, y, rng.normal(size=(7, 7)), method="akima")
+    assert not isinstance(obj._tabs, api._RecordTables)
+    lib = L.load()
+    kd = [torch.as_tensor(y, device="cuda")] * 2
+    narr = (C.c_int32 * 2)(7, 7)
+    fd = torch.zeros(49, dtype=torch.float64, device="cuda")
+    out = torch.zeros(49 * 4, dtype=torch.float64, device="cuda")
+    call = lambda nd, m: lib.ipx_slopes_pack_f64(nd, api._ptr_array(kd), narr, api._ptr(fd), 1, m, None,
+                                                 api._ptr(out), None)
+    assert call(2, L.IPX_SLOPE_CUBIC) == L.IPX_OK
+    assert call(2, L.IPX_SLOPE_AKIMA) == L.IPX_EUNSUPPORTED
+    assert call(1, L.IPX_SLOPE_CUBIC) == L.IPX_EUNSUPPORTED
+    assert call(2, 99) == L.IPX_EINVAL
+    assert call(4, L.IPX_SLOPE_CUBIC) == L.IPX_EINVAL
+    torch.cuda.synchronize()
+
+
 @pytest.mark.parametrize("n", [2, 3, 4, 25])
 def test_cubic2_boundary_conditions(n):
     rng = np.random.default_rng(5)
