@@ -230,6 +230,19 @@ int ipx_cell_order_f32(int32_t ndim, const float* const* q, int64_t nq, const fl
 int ipx_cell_order_f64(int32_t ndim, const double* const* q, int64_t nq, const double* const* knots,
                        const int32_t* n, int32_t periodic_mask, const ipx_params* params,
                        int32_t params_on_device, uint32_t* order, void* workspace, void* stream);
+/* ipx_cell_sort_*: ipx_cell_order_* plus the queries themselves in that order, q_sorted[ax][k] =
+ * q[ax][order[k]] (HOST array of ndim device pointers, nq elements each).  The coordinates
+ * ride through an interleaved copy in the workspace so the permutation reads one sector per
+ * query.  workspace: ipx_cell_sort_workspace_bytes(ndim, nq, sizeof(T)). */
+size_t ipx_cell_sort_workspace_bytes(int32_t ndim, int64_t nq, int32_t elem_size);
+int ipx_cell_sort_f32(int32_t ndim, const float* const* q, int64_t nq, const float* const* knots,
+                      const int32_t* n, int32_t periodic_mask, const ipx_params* params,
+                      int32_t params_on_device, uint32_t* order, float* const* q_sorted,
+                      void* workspace, void* stream);
+int ipx_cell_sort_f64(int32_t ndim, const double* const* q, int64_t nq, const double* const* knots,
+                      const int32_t* n, int32_t periodic_mask, const ipx_params* params,
+                      int32_t params_on_device, uint32_t* order, double* const* q_sorted,
+                      void* workspace, void* stream);
 int ipx_gather_f32(const float* src, const uint32_t* order, int64_t n, int64_t batch, float* dst,
                    void* stream);
 int ipx_gather_f64(const double* src, const uint32_t* order, int64_t n, int64_t batch, double* dst,

@@ -56,11 +56,12 @@ class SlopeOpts(C.Structure):
 
 # every symbol include/ipx.h declares; tests/test_abi.py checks the .so exports them all
 SYMBOLS = (
-    ["ipx_version", "ipx_build_info", "ipx_slopes_workspace_bytes", "ipx_cell_order_workspace_bytes"]
+    ["ipx_version", "ipx_build_info", "ipx_slopes_workspace_bytes", "ipx_cell_order_workspace_bytes",
+     "ipx_cell_sort_workspace_bytes"]
     + [f"ipx_eval{d}d_{t}" for d in (1, 2, 3) for t in ("f32", "f64")]
     + [
         f"ipx_{name}_{t}"
-        for name in ("bin_index", "slopes", "slopes_pack", "periodic_knots", "pad_periodic", "pack", "cell_order", "gather",
+        for name in ("bin_index", "slopes", "slopes_pack", "periodic_knots", "pad_periodic", "pack", "cell_order", "cell_sort", "gather",
                      "gather_multi", "scatter", "vjp_tables")
         for t in ("f32", "f64")
     ]
@@ -90,6 +91,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.ipx_slopes_workspace_bytes.argtypes = [i32, i32, i32]
     lib.ipx_cell_order_workspace_bytes.restype = C.c_size_t
     lib.ipx_cell_order_workspace_bytes.argtypes = [i64]
+    lib.ipx_cell_sort_workspace_bytes.restype = C.c_size_t
+    lib.ipx_cell_sort_workspace_bytes.argtypes = [i32, i64, i32]
     tail = [C.POINTER(vp), i32, i64, i32, i32, C.POINTER(Params), i32, vp, vp, vp]
     for t in ("f32", "f64"):
         f = getattr(lib, f"ipx_eval1d_{t}")
@@ -123,6 +126,10 @@ def _declare(lib: C.CDLL) -> None:
         f.restype = C.c_int
         f.argtypes = [i32, C.POINTER(vp), i64, C.POINTER(vp), C.POINTER(i32), i32, C.POINTER(Params), i32,
                       vp, vp, vp]
+        f = getattr(lib, f"ipx_cell_sort_{t}")
+        f.restype = C.c_int
+        f.argtypes = [i32, C.POINTER(vp), i64, C.POINTER(vp), C.POINTER(i32), i32, C.POINTER(Params), i32,
+                      vp, C.POINTER(vp), vp, vp]
         f = getattr(lib, f"ipx_vjp_tables_{t}")
         f.restype = C.c_int
         f.argtypes = [i32, C.POINTER(vp), i64, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), i64, i32, i32,

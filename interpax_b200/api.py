@@ -322,6 +322,21 @@ def _permute_dev(src: torch.Tensor, order: torch.Tensor, batch: int, gather: boo
     return dst
 
 
+def _cell_sort_dev(ndim, qs, knots, ns, periodic_mask, params):
+    """(order, queries in that order): ipx_cell_sort_*."""
+    lib = L.load()
+    nq = qs[0].numel()
+    order = torch.empty(nq, dtype=torch.int32, device=qs[0].device)  # holds uint32 values
+    out = [torch.empty_like(q) for q in qs]
+    wbytes = int(lib.ipx_cell_sort_workspace_bytes(ndim, nq, qs[0].element_size()))
+    ws = torch.empty(max(wbytes, 256), dtype=torch.uint8, device=qs[0].device)
+    fn = getattr(lib, f"ipx_cell_sort_{_suffix(qs[0])}")
+    narr = (C.c_int32 * ndim)(*[int(n) for n in ns])
+    L.check(fn(ndim, _ptr_array(qs), nq, _ptr_array(knots), narr, periodic_mask, C.byref(params), 0,
+               _ptr(order), _ptr_array(out), _ptr(ws), _stream()), "ipx_cell_sort")
+    return order, out
+
+
 def _presorted(launch, ndim, knots, ns, mask, params, batch):
     """Wrap `launch` so that it visits the queries in cell order: gather -> evaluate -> scatter
     (results are bit-identical to the plain call; only the memory access pattern changes)."""
@@ -331,11 +346,7 @@ def _presorted(launch, ndim, knots, ns, mask, params, batch):
         nq = dq[0].numel()
         if nq == 0:
             return launch(dq, dout, False)
-        order = _cell_order_dev(ndim, dq, knots, ns, mask, params)
-        qs = [torch.empty_like(q) for q in dq]
-        lib = L.load()
-        fn = getattr(lib, f"ipx_gather_multi_{_suffix(dq[0])}")
-        L.check(fn(ndim, _ptr_array(dq), _ptr(order), nq, _ptr_array(qs), _stream()), "ipx_gather_multi")
+        order, qs = _cell_sort_dev(ndim, dq, knots, ns, mask, params)
         tmp, _ = launch(qs, None, False)
         if dout is None:
             dout = torch.empty((nq, batch), dtype=tmp.dtype, device=tmp.device)

@@ -49,9 +49,14 @@ template <typename T, int ND> struct KeyArgs {
   const ipx_params* dp;
 };
 
+// Interleaved copy of the query coordinates, one record per query padded to a power of two
+// (3-D: x, y, z, 0), so that the random gather after the sort touches ONE 32-byte sector per
+// query instead of one per coordinate array.
+template <int ND> struct CoordRec { static constexpr int kLen = ND == 3 ? 4 : ND; };
+
 template <typename T, int ND>
 __global__ void cell_key_kernel(const KeyArgs<T, ND> a, uint32_t* __restrict__ keys,
-                                uint32_t* __restrict__ vals) {
+                                uint32_t* __restrict__ vals, T* __restrict__ recs) {
   __shared__ AxisConst<T> consts[ND];
   __shared__ ipx_params params_s;
   if (threadIdx.x < ND) axis_consts(a.ax[threadIdx.x], consts[threadIdx.x]);
@@ -70,6 +75,56 @@ __global__ void cell_key_kernel(const KeyArgs<T, ND> a, uint32_t* __restrict__ k
     }
     keys[e] = key;
     vals[e] = (uint32_t)e;
+    if (recs != nullptr) {
+      constexpr int R = CoordRec<ND>::kLen;
+      T c[R];
+#pragma unroll
+      for (int ax = 0; ax < R; ++ax) c[ax] = ax < ND ? a.ax[ax < ND ? ax : 0].q[e] : T(0);
+      T* r = recs + e * R;
+      if constexpr (R == 1) {
+        r[0] = c[0];
+      } else if constexpr (sizeof(T) == 8) {
+#pragma unroll
+        for (int m = 0; m < R; m += 2) *reinterpret_cast<double2*>(r + m) = make_double2(c[m], c[m + 1]);
+      } else if constexpr (R == 2) {
+        *reinterpret_cast<float2*>(r) = make_float2(c[0], c[1]);
+      } else {
+        *reinterpret_cast<float4*>(r) = make_float4(c[0], c[1], c[2], c[3]);
+      }
+    }
+  }
+}
+
+// dst[ax][k] = recs[order[k]][ax]: sequential writes, one random record read per query
+template <typename T, int ND> struct RecGatherArgs {
+  T* __restrict__ dst[ND];
+};
+
+template <typename T, int ND>
+__global__ void gather_records_kernel(const T* __restrict__ recs, const uint32_t* __restrict__ order,
+                                      int64_t n, const RecGatherArgs<T, ND> a) {
+  constexpr int R = CoordRec<ND>::kLen;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+    const T* r = recs + (int64_t)order[k] * R;
+    T c[R];
+    if constexpr (R == 1) {
+      c[0] = __ldg(r);
+    } else if constexpr (sizeof(T) == 8) {
+#pragma unroll
+      for (int m = 0; m < R; m += 2) {
+        const double2 v = __ldg(reinterpret_cast<const double2*>(r + m));
+        c[m] = v.x; c[m + 1] = v.y;
+      }
+    } else if constexpr (R == 2) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(r));
+      c[0] = v.x; c[1] = v.y;
+    } else {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(r));
+      c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+    }
+#pragma unroll
+    for (int ax = 0; ax < ND; ++ax) a.dst[ax][k] = c[ax];
   }
 }
 
@@ -289,7 +344,7 @@ static void radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_
 template <typename T, int ND>
 static int launch_cell_order(const T* const* q, int64_t nq, const T* const* knots, const int32_t* n,
                              int32_t periodic_mask, const ipx_params* params, int32_t params_on_device,
-                             uint32_t* order, void* workspace, cudaStream_t s) {
+                             uint32_t* order, T* const* q_sorted, void* workspace, cudaStream_t s) {
   KeyArgs<T, ND> a;
   double cells = 1.0;
   for (int ax = 0; ax < ND; ++ax) {
@@ -326,8 +381,20 @@ static int launch_cell_order(const T* const* q, int64_t nq, const T* const* knot
   uint32_t* sums = reinterpret_cast<uint32_t*>(ws + p.off_sums);
   int64_t need = (nq + 255) / 256;
   int64_t cap = (int64_t)sm_count() * 16;
-  cell_key_kernel<T, ND><<<(int)(need < cap ? need : cap), 256, 0, s>>>(a, keys_a, order);
+  T* recs = nullptr;
+  if (q_sorted != nullptr) {
+    for (int ax = 0; ax < ND; ++ax)
+      if (q_sorted[ax] == nullptr) return IPX_EINVAL;
+    recs = reinterpret_cast<T*>(ws + p.total);  // p.total is 256-byte aligned
+  }
+  cell_key_kernel<T, ND><<<(int)(need < cap ? need : cap), 256, 0, s>>>(a, keys_a, order, recs);
   radix_sort_pairs(keys_a, order, keys_b, vals_b, hist, sums, p, bits, s);
+  if (q_sorted != nullptr) {
+    RecGatherArgs<T, ND> g;
+    for (int ax = 0; ax < ND; ++ax) g.dst[ax] = q_sorted[ax];
+    int64_t gcap = (int64_t)sm_count() * 32;
+    gather_records_kernel<T, ND><<<(int)(need < gcap ? need : gcap), 256, 0, s>>>(recs, order, nq, g);
+  }
   return cudaPeekAtLastError() == cudaSuccess ? IPX_OK : IPX_ELAUNCH;
 }
 
@@ -419,16 +486,17 @@ static int launch_permute(const T* src, const uint32_t* order, int64_t n, int64_
 template <typename T>
 static int cell_order_dispatch(int32_t ndim, const T* const* q, int64_t nq, const T* const* knots,
                                const int32_t* n, int32_t periodic_mask, const ipx_params* params,
-                               int32_t params_on_device, uint32_t* order, void* workspace, void* stream) {
+                               int32_t params_on_device, uint32_t* order, T* const* q_sorted,
+                               void* workspace, void* stream) {
   if (ndim < 1 || ndim > 3 || q == nullptr || knots == nullptr || n == nullptr || params == nullptr || nq < 0)
     return IPX_EINVAL;
   if (nq >= 4294967296LL) return IPX_EUNSUPPORTED;
   if (nq == 0) return IPX_OK;
   if (order == nullptr || workspace == nullptr) return IPX_EINVAL;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (ndim == 1) return launch_cell_order<T, 1>(q, nq, knots, n, periodic_mask, params, params_on_device, order, workspace, s);
-  if (ndim == 2) return launch_cell_order<T, 2>(q, nq, knots, n, periodic_mask, params, params_on_device, order, workspace, s);
-  return launch_cell_order<T, 3>(q, nq, knots, n, periodic_mask, params, params_on_device, order, workspace, s);
+  if (ndim == 1) return launch_cell_order<T, 1>(q, nq, knots, n, periodic_mask, params, params_on_device, order, q_sorted, workspace, s);
+  if (ndim == 2) return launch_cell_order<T, 2>(q, nq, knots, n, periodic_mask, params, params_on_device, order, q_sorted, workspace, s);
+  return launch_cell_order<T, 3>(q, nq, knots, n, periodic_mask, params, params_on_device, order, q_sorted, workspace, s);
 }
 
 }  // namespace ipx
@@ -440,13 +508,34 @@ extern "C" int ipx_cell_order_f32(int32_t ndim, const float* const* q, int64_t n
                                   const int32_t* n, int32_t periodic_mask, const ipx_params* params,
                                   int32_t params_on_device, uint32_t* order, void* workspace, void* stream) {
   return ipx::cell_order_dispatch<float>(ndim, q, nq, knots, n, periodic_mask, params, params_on_device, order,
-                                         workspace, stream);
+                                         nullptr, workspace, stream);
+}
+extern "C" int ipx_cell_sort_f32(int32_t ndim, const float* const* q, int64_t nq, const float* const* knots,
+                                 const int32_t* n, int32_t periodic_mask, const ipx_params* params,
+                                 int32_t params_on_device, uint32_t* order, float* const* q_sorted,
+                                 void* workspace, void* stream) {
+  if (q_sorted == nullptr) return IPX_EINVAL;
+  return ipx::cell_order_dispatch<float>(ndim, q, nq, knots, n, periodic_mask, params, params_on_device, order,
+                                         q_sorted, workspace, stream);
 }
 extern "C" int ipx_cell_order_f64(int32_t ndim, const double* const* q, int64_t nq, const double* const* knots,
                                   const int32_t* n, int32_t periodic_mask, const ipx_params* params,
                                   int32_t params_on_device, uint32_t* order, void* workspace, void* stream) {
   return ipx::cell_order_dispatch<double>(ndim, q, nq, knots, n, periodic_mask, params, params_on_device, order,
-                                          workspace, stream);
+                                          nullptr, workspace, stream);
+}
+extern "C" int ipx_cell_sort_f64(int32_t ndim, const double* const* q, int64_t nq, const double* const* knots,
+                                 const int32_t* n, int32_t periodic_mask, const ipx_params* params,
+                                 int32_t params_on_device, uint32_t* order, double* const* q_sorted,
+                                 void* workspace, void* stream) {
+  if (q_sorted == nullptr) return IPX_EINVAL;
+  return ipx::cell_order_dispatch<double>(ndim, q, nq, knots, n, periodic_mask, params, params_on_device, order,
+                                          q_sorted, workspace, stream);
+}
+extern "C" size_t ipx_cell_sort_workspace_bytes(int32_t ndim, int64_t nq, int32_t elem_size) {
+  if (nq < 0) nq = 0;
+  const size_t rec = ndim == 3 ? 4 : (ndim < 1 ? 1 : (size_t)ndim);
+  return ipx::make_plan(nq).total + (size_t)nq * rec * (size_t)(elem_size == 4 ? 4 : 8);
 }
 extern "C" int ipx_gather_f32(const float* src, const uint32_t* order, int64_t n, int64_t batch, float* dst,
                               void* stream) {
