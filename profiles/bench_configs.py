@@ -2,7 +2,7 @@
 spot-check of each against the oracle.  bench.py measures the headline config (C4); this
 script is the evidence for the rest.  Writes one JSON object per config to stdout.
 
-    python profiles/bench_configs.py [c1] [c2] [c3] [c5]
+    python profiles/bench_configs.py [c1] [c2] [c3] [c4] [c5]
 """
 import json
 import os
@@ -80,6 +80,9 @@ def c2():
     xs = torch.sort(xq).values
     obuf = torch.empty((nq, B), dtype=torch.float64, device=dev)
     for method in ("linear", "cubic2", "monotonic", "akima"):
+        ip = ipx.Interpolator1D(x, fp, method)  # first use also loads the kernels' module
+        torch.cuda.synchronize()
+        del ip
         t0 = time.perf_counter()
         ip = ipx.Interpolator1D(x, fp, method)
         torch.cuda.synchronize()
@@ -173,9 +176,48 @@ def c5():
     return res
 
 
+def c4():
+    """Around the headline config (bench.py has the class call itself): construction, the
+    functional form that rebuilds the slopes on every call, and presorted random order."""
+    n, nq = 256, 100_000_000
+    P = 2 * np.pi
+    g = torch.Generator(device=dev).manual_seed(1238)
+    x = torch.arange(n, device=dev, dtype=torch.float64) * (P / n)
+    z = torch.linspace(0, 1, n, device=dev, dtype=torch.float64)
+    f = torch.randn((n, n, n), dtype=torch.float64, device=dev, generator=g)
+    extrap, period = ((True, True), (True, True), (True, 0.0)), (P, P, None)
+    ms_build = timed(lambda: ipx.Interpolator3D(x, x, z, f, "cubic", extrap, period), 10, 3)
+    ip = ipx.Interpolator3D(x, x, z, f, "cubic", extrap, period)
+    q = [(torch.rand(nq, dtype=torch.float64, device=dev, generator=g) * 3 - 1) * P for _ in range(2)]
+    q.append(torch.rand(nq, dtype=torch.float64, device=dev, generator=g) * 1.1 - 0.05)
+    cell = lambda v, per: (torch.remainder(v, per) / per * n).floor().long().clamp(0, n - 1)
+    key = (cell(q[0], P) * n + cell(q[1], P)) * n + (q[2].clamp(0, 1) * (n - 1)).floor().long()
+    o = torch.argsort(key)
+    del key
+    s = [a[o] for a in q]
+    del o
+    obuf = torch.empty(nq, dtype=torch.float64, device=dev)
+    ms_cls = timed(lambda: ip(*s, out=obuf), 5, 2)
+    ms_fun = timed(lambda: ipx.interp3d(*s, x, x, z, f, "cubic", 0, extrap, period, out=obuf), 5, 2)
+    ms_pre = timed(lambda: ip(*q, presort=True, out=obuf), 3, 2)
+    ms_rnd = timed(lambda: ip(*q, out=obuf), 3, 2)
+    m = 1 << 11
+    got = ipx.interp3d(*[a[:m] for a in s], x, x, z, f, "cubic", 0, extrap, period).cpu().numpy()
+    want = O.interp3d(*[a[:m].cpu().numpy() for a in s], x.cpu().numpy(), x.cpu().numpy(), z.cpu().numpy(),
+                      f.cpu().numpy(), "cubic", 0, extrap, period)
+    return {"config": "C4 tricubic 256^3 period+extrap, 1e8 queries, f64: around the headline",
+            "construct_ms": ms_build,
+            "class_call_sorted_queries_per_s": nq / ms_cls * 1e3,
+            "functional_call_sorted_queries_per_s": nq / ms_fun * 1e3,
+            "functional_call_ms": ms_fun, "class_call_ms": ms_cls,
+            "random_queries_per_s": nq / ms_rnd * 1e3,
+            "random_presorted_queries_per_s": nq / ms_pre * 1e3,
+            "parity_functional": parity(got, want, 1e-12)}
+
+
 if __name__ == "__main__":
-    which = [a.lower() for a in sys.argv[1:]] or ["c1", "c2", "c3", "c5"]
+    which = [a.lower() for a in sys.argv[1:]] or ["c1", "c2", "c3", "c4", "c5"]
     for name in which:
-        r = {"c1": c1, "c2": c2, "c3": c3, "c5": c5}[name]()
+        r = {"c1": c1, "c2": c2, "c3": c3, "c4": c4, "c5": c5}[name]()
         for item in (r if isinstance(r, list) else [r]):
             print(json.dumps(item), flush=True)
