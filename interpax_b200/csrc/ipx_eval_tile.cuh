@@ -28,6 +28,8 @@
 // is persistent): the interval lookup costs no global loads and the local coordinate no
 // division per query.  1/dx is produced by the same IEEE division as in the generic kernel.
 #pragma once
+#include <atomic>
+#include <cstdlib>
 
 namespace ipx {
 
@@ -110,9 +112,13 @@ __device__ __forceinline__ void cp_async_wait_all() {
 
 // DEVP: traced operands are read from device memory.  ORD0: every derivative order is 0 (known
 // on the host when the operands are host-resident), which drops the order switch from the loop.
-template <typename T, int ND, bool DEVP, bool ORD0, int RC>
+// TWO: two consecutive queries per lane (dense streams, several queries per cell: the pair
+// shares node layers); otherwise one per lane (sparse streams, about one query per cell or
+// fewer: a warp's queries then span fewer cells, fit one run and keep every lane busy).
+template <typename T, int ND, bool DEVP, bool ORD0, int RC, bool TWO = true>
 __global__ void __launch_bounds__(kTileThreads, sizeof(T) == 4 ? 3 : 2)
 eval_tile_kernel(const EvalArgs<T, ND> a) {
+  constexpr int QPL = TWO ? 2 : 1;  // queries per lane per round
   using Cfg = TileCfg<T, ND, RC>;
   constexpr int kRunCap = RC;
   constexpr int LPC = 32 / Cfg::NC;          // lanes that copy one column
@@ -389,17 +395,20 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
   };
 
   // ---- persistent loop: 64 consecutive queries per warp per round ------------------------
-  const int64_t step = (int64_t)gridDim.x * kTileThreads * 2;
-  const int64_t w0 = ((int64_t)blockIdx.x * kTileWarps + warp) * 64;  // warp's first query
+  const int64_t step = (int64_t)gridDim.x * kTileThreads * QPL;
+  const int64_t w0 = ((int64_t)blockIdx.x * kTileWarps + warp) * (32 * QPL);  // warp's first query
   if (w0 >= a.nq) return;  // whole warp idle (after the CTA barrier above)
   const int rounds = (int)((a.nq - w0 + step - 1) / step);
 
-  int64_t qa = w0 + 2 * lane;  // this lane's first query; its second is qa + 1
+  int64_t qa = w0 + QPL * lane;  // this lane's first query; its second (TWO) is qa + 1
   T qn[2][ND];
   auto prefetch = [&](int64_t q) {
 #pragma unroll
     for (int ax = 0; ax < ND; ++ax) {
-      if (q + 1 < a.nq) {  // q is even and the arrays are 16-byte aligned: one vector load
+      if constexpr (!TWO) {
+        qn[0][ax] = q < a.nq ? __ldcs(a.ax[ax].q + q) : T(0);
+        qn[1][ax] = T(0);
+      } else if (q + 1 < a.nq) {  // q is even and the arrays are 16-byte aligned: one vector load
         if (sizeof(T) == 8) {
           const double2 v = __ldcs(reinterpret_cast<const double2*>(a.ax[ax].q + q));
           qn[0][ax] = T(v.x); qn[1][ax] = T(v.y);
@@ -417,7 +426,7 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
 
   for (int round = 0; round < rounds; ++round, qa += step) {
     const bool act_a = qa < a.nq;
-    const bool act_b = qa + 1 < a.nq;
+    const bool act_b = TWO && qa + 1 < a.nq;
     T qc[2][ND];
 #pragma unroll
     for (int k = 0; k < 2; ++k)
@@ -430,10 +439,11 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
     if constexpr (ND == 3) {
       T cell[ND][3];
       locate_q(qc[0], SS[0], pzz[0], cell, nullptr);
-      locate_q(qc[1], SS[1], pzz[1], cell, &SS[0]);
+      if constexpr (TWO) locate_q(qc[1], SS[1], pzz[1], cell, &SS[0]);
     } else {
-      locate_range(qc, SS, pzz, 0, 2);
+      locate_range(qc, SS, pzz, 0, QPL);
     }
+    if constexpr (!TWO) { SS[1] = SS[0]; pzz[1] = pzz[0]; }
     QState<T, ND>& Sa = SS[0];
     QState<T, ND>& Sb = SS[1];
     const int pza = pzz[0], pzb = pzz[1];
@@ -557,13 +567,42 @@ template <typename T, int ND, int RC> static size_t tile_smem_bytes(const EvalAr
   return knots + (size_t)kTileWarps * TileCfg<T, ND, RC>::WARP_TILE_BYTES;
 }
 
-template <typename T, int ND, int RC>
+template <typename T, int ND, int RC> static int tile_ctas_per_sm_query(size_t smem);
+
+// resident CTAs per SM for a run capacity (register- or shared-memory-bound)
+template <typename T, int ND, int RC> static int tile_ctas_per_sm(const EvalArgs<T, ND>& a) {
+  const size_t smem = tile_smem_bytes<T, ND, RC>(a);
+  // the answer depends on the shared-memory size only; remember the last one, size and
+  // answer packed in one atomic word so concurrent callers never see a mixed pair
+  static std::atomic<unsigned long long> last{~0ull};
+  const unsigned long long seen = last.load(std::memory_order_relaxed);
+  if ((seen >> 8) == (unsigned long long)smem) return (int)(seen & 0xff);
+  const int ctas = tile_ctas_per_sm_query<T, ND, RC>(smem);
+  last.store(((unsigned long long)smem << 8) | (unsigned)(ctas & 0xff), std::memory_order_relaxed);
+  return ctas;
+}
+
+template <typename T, int ND, int RC> static int tile_ctas_per_sm_query(size_t smem) {
+  auto kern = eval_tile_kernel<T, ND, false, true, RC, true>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return 0;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, smem) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return per_sm;
+}
+
+template <typename T, int ND, int RC, bool TWO = true>
 static bool launch_tile_rc(const EvalArgs<T, ND>& a, cudaStream_t s) {
+  constexpr int QPL = TWO ? 2 : 1;
   const size_t smem = tile_smem_bytes<T, ND, RC>(a);
   bool ord0 = a.dp == nullptr;
   for (int ax = 0; ax < ND && ord0; ++ax) ord0 = a.hp.axis[ax].derivative <= 0;
-  auto kern = a.dp ? eval_tile_kernel<T, ND, true, false, RC>
-                   : (ord0 ? eval_tile_kernel<T, ND, false, true, RC> : eval_tile_kernel<T, ND, false, false, RC>);
+  auto kern = a.dp ? eval_tile_kernel<T, ND, true, false, RC, TWO>
+                   : (ord0 ? eval_tile_kernel<T, ND, false, true, RC, TWO>
+                           : eval_tile_kernel<T, ND, false, false, RC, TWO>);
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return false;
   int dev = 0, sms = 148, per_sm = 1;
@@ -571,7 +610,7 @@ static bool launch_tile_rc(const EvalArgs<T, ND>& a, cudaStream_t s) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, smem);
   if (per_sm < 1) per_sm = 1;
-  int64_t need = (a.nq + 2 * kTileThreads - 1) / (2 * kTileThreads);
+  int64_t need = (a.nq + QPL * kTileThreads - 1) / (QPL * kTileThreads);
   int64_t grid = (int64_t)sms * per_sm;  // persistent: one resident wave
   if (need < grid) grid = need;
   kern<<<(int)grid, kTileThreads, smem, s>>>(a);
@@ -597,12 +636,27 @@ static bool launch_tile(const EvalArgs<T, ND>& a, cudaStream_t s) {
     }
     if (total_knots > kSmemKnotCap) return false;
     if ((reinterpret_cast<uintptr_t>(a.tab[0]) & 15) != 0) return false;
-    // queries per cell decides how long a run the tile must hold: few queries per cell means
-    // a warp's 64 consecutive (sorted) queries span many cells along the last axis
+    // Queries per cell decide the shape of a warp's round (measured on 256^3 / 512^3 f64,
+    // profiles/sweep_tile_modes.sh): from about three per cell up, two consecutive queries
+    // per lane share node layers; below that a lane's pair is rarely in adjacent cells and a
+    // warp's 64 queries span several runs, so one query per lane keeps every lane busy.  The
+    // long run (32 nodes) pays off below about five queries per cell (a round spans more than
+    // 16 nodes); denser streams keep the short one, which leaves more of the SM's memory to L1
+    // for the direct gathers of incoherent (random-order) warps.
     double cells = 1.0;
     for (int ax = 0; ax < ND; ++ax) cells *= (double)(a.ax[ax].n > 1 ? a.ax[ax].n - 1 : 1);
-    const bool sparse = (double)a.nq < 2.0 * cells;
-    return sparse ? launch_tile_rc<T, ND, 32>(a, s) : launch_tile_rc<T, ND, 16>(a, s);
+    const bool two = (double)a.nq >= 3.0 * cells;
+    const bool long_run = (double)a.nq < 5.0 * cells &&
+                          tile_ctas_per_sm<T, ND, 32>(a) >= tile_ctas_per_sm<T, ND, 16>(a);
+    const char* e = getenv("IPX_TILE_MODE");  // experiment switch (profiles/sweep_tile_modes.sh)
+    if (e != nullptr) {
+      if (e[0] == 'a') return launch_tile_rc<T, ND, 16, true>(a, s);
+      if (e[0] == 'b') return launch_tile_rc<T, ND, 16, false>(a, s);
+      if (e[0] == 'c') return launch_tile_rc<T, ND, 32, true>(a, s);
+      if (e[0] == 'd') return launch_tile_rc<T, ND, 32, false>(a, s);
+    }
+    if (long_run) return two ? launch_tile_rc<T, ND, 32, true>(a, s) : launch_tile_rc<T, ND, 32, false>(a, s);
+    return two ? launch_tile_rc<T, ND, 16, true>(a, s) : launch_tile_rc<T, ND, 16, false>(a, s);
   }
 }
 
