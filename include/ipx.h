@@ -277,6 +277,45 @@ int ipx_vjp_tables_f64(int32_t ndim, const double* const* q, int64_t nq, const d
                        int32_t params_on_device, const double* cotangent, double* const* grad_tables,
                        void* stream);
 
+/* ---------------------------------------------------------------------------------
+ * Piecewise polynomials in the power basis (interpax/_ppoly.py).  Coefficients as the
+ * reference holds them after its moveaxis: c[(j*m + i)*batch + b] multiplies
+ * (x - x[i])^(k-1-j) on piece i, for trailing element b; x has m+1 breakpoints.
+ *
+ * ipx_ppoly_eval_*: PPoly.__call__ (_ppoly.py:189-257): out[q*batch + b] = nu-th derivative of
+ *   piece clip(searchsorted(x, q, "right"), 1, m) at q (zero when nu >= k).
+ *   extrap: IPX_PPOLY_NAN (NaN outside [x[0], x[m]]), IPX_PPOLY_EXTRAPOLATE (end pieces
+ *   extended), IPX_PPOLY_PERIODIC (q -> x[0] + (q - x[0]) mod (x[m] - x[0]) first).
+ *   idx_out: optional, the piece index + 1 (int32, nq).  k <= 64.
+ * ipx_ppoly_from_hermite_*: CubicHermiteSpline.__init__ (_ppoly.py:540-569): values y and
+ *   slopes dydx at the n knots, shape (n, batch), -> c of shape (4, n-1, batch).
+ * ipx_ppoly_derivative_*: coefficients of PPoly.derivative(nu) (_ppoly.py:259-296), 0 <= nu < k:
+ *   c2 of shape (k-nu, m, batch).
+ * ipx_ppoly_antiderivative_*: ONE step of PPoly.antiderivative (_ppoly.py:328-339): c2 of shape
+ *   (k+1, m, batch), continuous across the breakpoints (constants accumulated left to right).
+ * --------------------------------------------------------------------------------- */
+#define IPX_PPOLY_NAN 0
+#define IPX_PPOLY_EXTRAPOLATE 1
+#define IPX_PPOLY_PERIODIC 2
+int ipx_ppoly_eval_f32(const float* c, int32_t k, int32_t m, int64_t batch, const float* x,
+                       const float* q, int64_t nq, int32_t nu, int32_t extrap, float* out,
+                       int32_t* idx_out, void* stream);
+int ipx_ppoly_eval_f64(const double* c, int32_t k, int32_t m, int64_t batch, const double* x,
+                       const double* q, int64_t nq, int32_t nu, int32_t extrap, double* out,
+                       int32_t* idx_out, void* stream);
+int ipx_ppoly_from_hermite_f32(const float* x, int32_t n, const float* y, const float* dydx,
+                               int64_t batch, float* c, void* stream);
+int ipx_ppoly_from_hermite_f64(const double* x, int32_t n, const double* y, const double* dydx,
+                               int64_t batch, double* c, void* stream);
+int ipx_ppoly_derivative_f32(const float* c, int32_t k, int32_t m, int64_t batch, int32_t nu,
+                             float* c2, void* stream);
+int ipx_ppoly_derivative_f64(const double* c, int32_t k, int32_t m, int64_t batch, int32_t nu,
+                             double* c2, void* stream);
+int ipx_ppoly_antiderivative_f32(const float* c, int32_t k, int32_t m, int64_t batch,
+                                 const float* x, float* c2, void* stream);
+int ipx_ppoly_antiderivative_f64(const double* c, int32_t k, int32_t m, int64_t batch,
+                                 const double* x, double* c2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

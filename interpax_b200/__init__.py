@@ -1,5 +1,5 @@
 """interpax_b200 -- the query-evaluation path of interpax (interp1d/2d/3d, Interpolator1D/2D/3D,
-approx_df) as hand-written CUDA for B200 (sm_100a) behind a C ABI (include/ipx.h).
+approx_df, and the PPoly / CubicSpline family) as hand-written CUDA for B200 (sm_100a) behind a C ABI (include/ipx.h).
 
 Importing the package does not need a GPU; calling any function does, and raises if the CUDA
 library or a CUDA device is missing (there is no CPU fallback).
@@ -21,8 +21,14 @@ from .api import (
     interp3d,
     vjp_tables,
 )
+from .ppoly import Akima1DInterpolator, CubicHermiteSpline, CubicSpline, PchipInterpolator, PPoly
 
 __all__ = [
+    "Akima1DInterpolator",
+    "CubicHermiteSpline",
+    "CubicSpline",
+    "PchipInterpolator",
+    "PPoly",
     "approx_df",
     "bin_index",
     "Interpolator1D",

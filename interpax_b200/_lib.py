@@ -17,6 +17,7 @@ IPX_NEAREST, IPX_LINEAR, IPX_CUBIC = 0, 1, 2
 IPX_SOA, IPX_AOS = 0, 1
 IPX_SLOPE_CUBIC, IPX_SLOPE_CUBIC2, IPX_SLOPE_CARDINAL = 0, 1, 2
 IPX_SLOPE_MONOTONIC, IPX_SLOPE_MONOTONIC0, IPX_SLOPE_AKIMA, IPX_SLOPE_ZERO = 3, 4, 5, 6
+IPX_PPOLY_NAN, IPX_PPOLY_EXTRAPOLATE, IPX_PPOLY_PERIODIC = 0, 1, 2
 IPX_BC_NOT_A_KNOT, IPX_BC_FIRST, IPX_BC_SECOND = 0, 1, 2
 
 
@@ -62,7 +63,8 @@ SYMBOLS = (
     + [
         f"ipx_{name}_{t}"
         for name in ("bin_index", "slopes", "slopes_pack", "periodic_knots", "pad_periodic", "pack", "cell_order", "cell_sort", "gather",
-                     "gather_multi", "scatter", "vjp_tables")
+                     "gather_multi", "scatter", "vjp_tables", "ppoly_eval", "ppoly_from_hermite",
+                     "ppoly_derivative", "ppoly_antiderivative")
         for t in ("f32", "f64")
     ]
 )
@@ -130,6 +132,18 @@ def _declare(lib: C.CDLL) -> None:
         f.restype = C.c_int
         f.argtypes = [i32, C.POINTER(vp), i64, C.POINTER(vp), C.POINTER(i32), i32, C.POINTER(Params), i32,
                       vp, C.POINTER(vp), vp, vp]
+        f = getattr(lib, f"ipx_ppoly_eval_{t}")
+        f.restype = C.c_int
+        f.argtypes = [vp, i32, i32, i64, vp, vp, i64, i32, i32, vp, vp, vp]
+        f = getattr(lib, f"ipx_ppoly_from_hermite_{t}")
+        f.restype = C.c_int
+        f.argtypes = [vp, i32, vp, vp, i64, vp, vp]
+        f = getattr(lib, f"ipx_ppoly_derivative_{t}")
+        f.restype = C.c_int
+        f.argtypes = [vp, i32, i32, i64, i32, vp, vp]
+        f = getattr(lib, f"ipx_ppoly_antiderivative_{t}")
+        f.restype = C.c_int
+        f.argtypes = [vp, i32, i32, i64, vp, vp, vp]
         f = getattr(lib, f"ipx_vjp_tables_{t}")
         f.restype = C.c_int
         f.argtypes = [i32, C.POINTER(vp), i64, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), i64, i32, i32,
