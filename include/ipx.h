@@ -284,6 +284,9 @@ int ipx_vjp_tables_f64(int32_t ndim, const double* const* q, int64_t nq, const d
  *
  * ipx_ppoly_eval_*: PPoly.__call__ (_ppoly.py:189-257): out[q*batch + b] = nu-th derivative of
  *   piece clip(searchsorted(x, q, "right"), 1, m) at q (zero when nu >= k).
+ *   layout: IPX_SOA = the (k, m, batch) array above; IPX_AOS = the piece-major copy (m, k)
+ *   written by ipx_ppoly_pack_* (batch == 1 only: the k coefficients of a piece share a sector,
+ *   which is what random-order queries pay for).
  *   extrap: IPX_PPOLY_NAN (NaN outside [x[0], x[m]]), IPX_PPOLY_EXTRAPOLATE (end pieces
  *   extended), IPX_PPOLY_PERIODIC (q -> x[0] + (q - x[0]) mod (x[m] - x[0]) first).
  *   idx_out: optional, the piece index + 1 (int32, nq).  k <= 64.
@@ -297,12 +300,14 @@ int ipx_vjp_tables_f64(int32_t ndim, const double* const* q, int64_t nq, const d
 #define IPX_PPOLY_NAN 0
 #define IPX_PPOLY_EXTRAPOLATE 1
 #define IPX_PPOLY_PERIODIC 2
-int ipx_ppoly_eval_f32(const float* c, int32_t k, int32_t m, int64_t batch, const float* x,
-                       const float* q, int64_t nq, int32_t nu, int32_t extrap, float* out,
-                       int32_t* idx_out, void* stream);
-int ipx_ppoly_eval_f64(const double* c, int32_t k, int32_t m, int64_t batch, const double* x,
-                       const double* q, int64_t nq, int32_t nu, int32_t extrap, double* out,
-                       int32_t* idx_out, void* stream);
+int ipx_ppoly_eval_f32(const float* c, int32_t layout, int32_t k, int32_t m, int64_t batch,
+                       const float* x, const float* q, int64_t nq, int32_t nu, int32_t extrap,
+                       float* out, int32_t* idx_out, void* stream);
+int ipx_ppoly_eval_f64(const double* c, int32_t layout, int32_t k, int32_t m, int64_t batch,
+                       const double* x, const double* q, int64_t nq, int32_t nu, int32_t extrap,
+                       double* out, int32_t* idx_out, void* stream);
+int ipx_ppoly_pack_f32(const float* c, int32_t k, int32_t m, float* out, void* stream);
+int ipx_ppoly_pack_f64(const double* c, int32_t k, int32_t m, double* out, void* stream);
 int ipx_ppoly_from_hermite_f32(const float* x, int32_t n, const float* y, const float* dydx,
                                int64_t batch, float* c, void* stream);
 int ipx_ppoly_from_hermite_f64(const double* x, int32_t n, const double* y, const double* dydx,

@@ -63,7 +63,7 @@ SYMBOLS = (
     + [
         f"ipx_{name}_{t}"
         for name in ("bin_index", "slopes", "slopes_pack", "periodic_knots", "pad_periodic", "pack", "cell_order", "cell_sort", "gather",
-                     "gather_multi", "scatter", "vjp_tables", "ppoly_eval", "ppoly_from_hermite",
+                     "gather_multi", "scatter", "vjp_tables", "ppoly_eval", "ppoly_pack", "ppoly_from_hermite",
                      "ppoly_derivative", "ppoly_antiderivative")
         for t in ("f32", "f64")
     ]
@@ -134,7 +134,10 @@ def _declare(lib: C.CDLL) -> None:
                       vp, C.POINTER(vp), vp, vp]
         f = getattr(lib, f"ipx_ppoly_eval_{t}")
         f.restype = C.c_int
-        f.argtypes = [vp, i32, i32, i64, vp, vp, i64, i32, i32, vp, vp, vp]
+        f.argtypes = [vp, i32, i32, i32, i64, vp, vp, i64, i32, i32, vp, vp, vp]
+        f = getattr(lib, f"ipx_ppoly_pack_{t}")
+        f.restype = C.c_int
+        f.argtypes = [vp, i32, i32, vp, vp]
         f = getattr(lib, f"ipx_ppoly_from_hermite_{t}")
         f.restype = C.c_int
         f.argtypes = [vp, i32, vp, vp, i64, vp, vp]

@@ -39,36 +39,129 @@ template <typename T> __device__ __forceinline__ T falling(int p, int nu) {
 
 // ------------------------------------------------------------------ evaluation
 // extrap: 0 = NaN outside [x[0], x[m]], 1 = extend the end pieces, 2 = periodic
-template <typename T, bool B1>
-__global__ void ppoly_eval_kernel(const T* __restrict__ c, int k, int m, int64_t batch,
-                                  const T* __restrict__ x, const T* __restrict__ q, int64_t nq, int nu,
-                                  int extrap, T* __restrict__ out, int32_t* __restrict__ idx_out) {
-  const int n = m + 1;
-  const T x0 = x[0], xe = x[m];
-  const T inv_h = xe > x0 ? T(m) / (xe - x0) : T(0);
-  const int64_t total = nq * batch;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int terms = k - nu;  // coefficients that survive the derivative
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-    const int64_t iq = B1 ? e : e / batch;
-    const int64_t b = B1 ? 0 : e - iq * batch;
-    T v = q[iq];
-    if (extrap == 2) v = x0 + py_mod(v - x0, xe - x0);  // _ppoly.py:233-235
-    T lo, hi;
-    const int i = bin_index(x, n, v, x0, inv_h, lo, hi);  // :239
-    const T t = v - lo;                                    // :241
-    const T* cp = c + (int64_t)(i - 1) * batch + b;
-    const int64_t cs = (int64_t)m * batch;
-    T y = T(0);
-    if (nu == 0) {
-      for (int j = 0; j < terms; ++j) y = add_rn(mul_rn(y, t), __ldg(cp + j * cs));
-    } else {
-      for (int j = 0; j < terms; ++j)
-        y = add_rn(mul_rn(y, t), mul_rn(__ldg(cp + j * cs), falling<T>(k - 1 - j, nu)));
+//
+// Coefficient (j, i, b) lives at c[j * sj + i * si + b]: the reference's layout (k, m, batch) has
+// sj = m * batch, si = batch; the piece-major copy ipx_ppoly_pack_* writes for scalar-valued
+// polynomials, (m, k), has sj = 1, si = k, so the k coefficients of a piece share a sector.
+template <typename T> struct PolyArgs {
+  const T* __restrict__ c;
+  const T* __restrict__ x;
+  const T* __restrict__ q;
+  T* __restrict__ out;
+  int32_t* __restrict__ idx_out;
+  int64_t sj, si, batch, nq;
+  int32_t k, m, nu, extrap;
+};
+
+template <typename T> struct PolyLoc {
+  T t;
+  int i;
+  bool outside;
+};
+
+template <typename T>
+__device__ __forceinline__ PolyLoc<T> poly_locate(const PolyArgs<T>& a, T v, T x0, T xe, T inv_h) {
+  PolyLoc<T> L;
+  if (a.extrap == 2) v = x0 + py_mod(v - x0, xe - x0);  // _ppoly.py:233-235
+  T lo, hi;
+  L.i = bin_index(a.x, a.m + 1, v, x0, inv_h, lo, hi);  // :239
+  L.t = v - lo;                                          // :241
+  L.outside = a.extrap != 1 && (v > xe || v < x0);       // :250-253
+  return L;
+}
+
+template <typename T>
+__device__ __forceinline__ T poly_horner(const PolyArgs<T>& a, const T* __restrict__ cp, T t) {
+  const int terms = a.k - a.nu;  // coefficients that survive the derivative
+  T y = T(0);
+  if (a.nu == 0) {
+    for (int j = 0; j < terms; ++j) y = add_rn(mul_rn(y, t), __ldg(cp + j * a.sj));
+  } else {
+    for (int j = 0; j < terms; ++j)
+      y = add_rn(mul_rn(y, t), mul_rn(__ldg(cp + j * a.sj), falling<T>(a.k - 1 - j, a.nu)));
+  }
+  return y;
+}
+
+// scalar-valued polynomials (batch == 1): one query per thread, kPolyUnroll of them in flight
+constexpr int kPolyUnroll = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(kPolyThreads) ppoly_eval_scalar_kernel(const PolyArgs<T> a) {
+  const T x0 = a.x[0], xe = a.x[a.m];
+  const T inv_h = xe > x0 ? T(a.m) / (xe - x0) : T(0);
+  const int64_t span = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e0 < a.nq; e0 += span * kPolyUnroll) {
+    T v[kPolyUnroll];
+#pragma unroll
+    for (int u = 0; u < kPolyUnroll; ++u) {
+      const int64_t e = e0 + u * span;
+      v[u] = e < a.nq ? __ldcs(a.q + e) : T(0);
     }
-    if (extrap != 1 && (v > xe || v < x0)) y = T(CUDART_NAN);  // :250-253
-    out[e] = y;
-    if (idx_out != nullptr && b == 0) idx_out[iq] = i;
+    PolyLoc<T> L[kPolyUnroll];
+#pragma unroll
+    for (int u = 0; u < kPolyUnroll; ++u) L[u] = poly_locate(a, v[u], x0, xe, inv_h);
+#pragma unroll
+    for (int u = 0; u < kPolyUnroll; ++u) {
+      const int64_t e = e0 + u * span;
+      if (e >= a.nq) continue;
+      T y = poly_horner(a, a.c + (int64_t)(L[u].i - 1) * a.si, L[u].t);
+      if (L[u].outside) y = T(CUDART_NAN);
+      __stcs(a.out + e, y);
+      if (a.idx_out != nullptr) a.idx_out[e] = L[u].i;
+    }
+  }
+}
+
+// vector-valued polynomials: a warp owns a query, lanes stride over the trailing elements
+// (coalesced coefficient reads and result writes; one lookup per query, not per element)
+template <typename T>
+__global__ void __launch_bounds__(kPolyThreads) ppoly_eval_rows_kernel(const PolyArgs<T> a) {
+  const T x0 = a.x[0], xe = a.x[a.m];
+  const T inv_h = xe > x0 ? T(a.m) / (xe - x0) : T(0);
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t iq = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); iq < a.nq; iq += warps) {
+    const PolyLoc<T> L = poly_locate(a, __ldg(a.q + iq), x0, xe, inv_h);  // warp-uniform
+    const T* row = a.c + (int64_t)(L.i - 1) * a.si;
+    T* orow = a.out + iq * a.batch;
+    for (int64_t b = lane; b < a.batch; b += 32) {
+      T y = poly_horner(a, row + b, L.t);
+      if (L.outside) y = T(CUDART_NAN);
+      __stcs(orow + b, y);
+    }
+    if (a.idx_out != nullptr && lane == 0) a.idx_out[iq] = L.i;
+  }
+}
+
+// few trailing elements: one (query, element) per thread
+template <typename T>
+__global__ void __launch_bounds__(kPolyThreads) ppoly_eval_elem_kernel(const PolyArgs<T> a) {
+  const T x0 = a.x[0], xe = a.x[a.m];
+  const T inv_h = xe > x0 ? T(a.m) / (xe - x0) : T(0);
+  const int64_t total = a.nq * a.batch;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int B = (int)a.batch;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int64_t iq = e / B;
+    const int b = (int)(e - iq * B);
+    const PolyLoc<T> L = poly_locate(a, __ldg(a.q + iq), x0, xe, inv_h);
+    T y = poly_horner(a, a.c + (int64_t)(L.i - 1) * a.si + b, L.t);
+    if (L.outside) y = T(CUDART_NAN);
+    a.out[e] = y;
+    if (a.idx_out != nullptr && b == 0) a.idx_out[iq] = L.i;
+  }
+}
+
+// (k, m) -> (m, k): the k coefficients of a piece contiguous
+template <typename T>
+__global__ void ppoly_pack_kernel(const T* __restrict__ c, int k, int64_t m, T* __restrict__ out) {
+  const int64_t total = (int64_t)k * m;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int64_t i = e / k;
+    const int j = (int)(e - i * k);
+    out[e] = c[(int64_t)j * m + i];
   }
 }
 
@@ -149,19 +242,37 @@ __global__ void ppoly_continuity_kernel(int k, int m, int64_t batch, T* __restri
 }
 
 template <typename T>
-static int launch_ppoly_eval(const T* c, int32_t k, int32_t m, int64_t batch, const T* x, const T* q,
-                             int64_t nq, int32_t nu, int32_t extrap, T* out, int32_t* idx_out,
+static int launch_ppoly_eval(const T* c, int32_t layout, int32_t k, int32_t m, int64_t batch, const T* x,
+                             const T* q, int64_t nq, int32_t nu, int32_t extrap, T* out, int32_t* idx_out,
                              void* stream) {
   if (k < 1 || k > kPolyMaxOrder || m < 1 || batch < 0 || nq < 0 || nu < 0 || extrap < 0 || extrap > 2)
     return IPX_EINVAL;
+  if (layout != IPX_SOA && layout != IPX_AOS) return IPX_EINVAL;
+  if (layout == IPX_AOS && batch != 1) return IPX_EUNSUPPORTED;  // piece-major copies are scalar-valued
   if (nq == 0 || batch == 0) return IPX_OK;
   if (c == nullptr || x == nullptr || q == nullptr || out == nullptr) return IPX_EINVAL;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int grid = poly_grid(nq * batch);
-  if (batch == 1)
-    ppoly_eval_kernel<T, true><<<grid, kPolyThreads, 0, s>>>(c, k, m, batch, x, q, nq, nu, extrap, out, idx_out);
-  else
-    ppoly_eval_kernel<T, false><<<grid, kPolyThreads, 0, s>>>(c, k, m, batch, x, q, nq, nu, extrap, out, idx_out);
+  PolyArgs<T> a;
+  a.c = c; a.x = x; a.q = q; a.out = out; a.idx_out = idx_out;
+  a.batch = batch; a.nq = nq; a.k = k; a.m = m; a.nu = nu; a.extrap = extrap;
+  a.sj = layout == IPX_AOS ? 1 : (int64_t)m * batch;
+  a.si = layout == IPX_AOS ? k : batch;
+  if (batch == 1) {
+    ppoly_eval_scalar_kernel<T><<<poly_grid((nq + kPolyUnroll - 1) / kPolyUnroll), kPolyThreads, 0, s>>>(a);
+  } else if (batch >= 16) {
+    ppoly_eval_rows_kernel<T><<<poly_grid(nq * 32), kPolyThreads, 0, s>>>(a);
+  } else {
+    ppoly_eval_elem_kernel<T><<<poly_grid(nq * batch), kPolyThreads, 0, s>>>(a);
+  }
+  return cudaPeekAtLastError() == cudaSuccess ? IPX_OK : IPX_ELAUNCH;
+}
+
+template <typename T>
+static int launch_ppoly_pack(const T* c, int32_t k, int32_t m, T* out, void* stream) {
+  if (k < 1 || m < 1) return IPX_EINVAL;
+  if (c == nullptr || out == nullptr) return IPX_EINVAL;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ppoly_pack_kernel<T><<<poly_grid((int64_t)k * m), kPolyThreads, 0, s>>>(c, k, m, out);
   return cudaPeekAtLastError() == cudaSuccess ? IPX_OK : IPX_ELAUNCH;
 }
 
@@ -203,10 +314,15 @@ static int launch_ppoly_antiderivative(const T* c, int32_t k, int32_t m, int64_t
 }  // namespace ipx
 
 #define IPX_PPOLY_DEFS(SUF, T)                                                                      \
-  extern "C" int ipx_ppoly_eval_##SUF(const T* c, int32_t k, int32_t m, int64_t batch, const T* x,  \
-                                      const T* q, int64_t nq, int32_t nu, int32_t extrap, T* out,   \
-                                      int32_t* idx_out, void* stream) {                             \
-    return ipx::launch_ppoly_eval<T>(c, k, m, batch, x, q, nq, nu, extrap, out, idx_out, stream);    \
+  extern "C" int ipx_ppoly_eval_##SUF(const T* c, int32_t layout, int32_t k, int32_t m,             \
+                                      int64_t batch, const T* x, const T* q, int64_t nq,            \
+                                      int32_t nu, int32_t extrap, T* out, int32_t* idx_out,         \
+                                      void* stream) {                                               \
+    return ipx::launch_ppoly_eval<T>(c, layout, k, m, batch, x, q, nq, nu, extrap, out, idx_out,     \
+                                     stream);                                                       \
+  }                                                                                                 \
+  extern "C" int ipx_ppoly_pack_##SUF(const T* c, int32_t k, int32_t m, T* out, void* stream) {     \
+    return ipx::launch_ppoly_pack<T>(c, k, m, out, stream);                                          \
   }                                                                                                 \
   extern "C" int ipx_ppoly_from_hermite_##SUF(const T* x, int32_t n, const T* y, const T* dydx,     \
                                               int64_t batch, T* c, void* stream) {                  \

@@ -115,6 +115,16 @@ class PPoly:
         batch = int(np.prod(ct.shape[2:], dtype=np.int64))
         return ct, k, m, batch
 
+    def _piece_major(self, ct, k, m):
+        """(m, k) copy of scalar-valued coefficients, built once per dtype (ipx_ppoly_pack_*)"""
+        cache = self.__dict__.setdefault("_packed", {})
+        if ct.dtype not in cache:
+            out = torch.empty((m, k), dtype=ct.dtype, device=ct.device)
+            fn = getattr(L.load(), f"ipx_ppoly_pack_{_suffix(ct)}")
+            L.check(fn(_ptr(ct), k, m, _ptr(out), _stream()), "ipx_ppoly_pack")
+            cache[ct.dtype] = out
+        return cache[ct.dtype]
+
     def __call__(self, x, nu=0, extrapolate=None):
         """Evaluate the piecewise polynomial or its nu-th derivative (_ppoly.py:189-257).
         Result shape: the shape of ``x`` in place of the interpolation axis."""
@@ -137,9 +147,13 @@ class PPoly:
         mode = L.IPX_PPOLY_PERIODIC if extrapolate == "periodic" else (
             L.IPX_PPOLY_EXTRAPOLATE if extrapolate else L.IPX_PPOLY_NAN)
         out = torch.empty((xq.numel(), batch), dtype=ct.dtype, device=dev)
+        layout = L.IPX_SOA
+        if batch == 1 and k > 1 and xq.numel() >= 4 * m:
+            # many queries on a scalar-valued polynomial: evaluate from the piece-major copy
+            ct, layout = self._piece_major(ct, k, m), L.IPX_AOS
         fn = getattr(L.load(), f"ipx_ppoly_eval_{_suffix(ct)}")
-        L.check(fn(_ptr(ct), k, m, batch, _ptr(knots), _ptr(xq), xq.numel(), int(nu), mode, _ptr(out), None,
-                   _stream()), "ipx_ppoly_eval")
+        L.check(fn(_ptr(ct), layout, k, m, batch, _ptr(knots), _ptr(xq), xq.numel(), int(nu), mode, _ptr(out),
+                   None, _stream()), "ipx_ppoly_eval")
         tail = tuple(self._c.shape[2:])
         if self._c.is_complex():
             out = torch.view_as_complex(out.reshape(x_shape + tail + (2,)))

@@ -189,3 +189,19 @@ def test_ppoly_large_stream():
     ref = O.CubicSpline(x.cpu().numpy(), y.cpu().numpy())
     close(r[:4096].cpu().numpy(), ref(sub), 1e-11)
     close(cs(xq[:4096], 1).cpu().numpy(), ref(sub, 1), 1e-10)
+
+
+def test_ppoly_piece_major_copy_is_bitwise_neutral():
+    # many queries on a scalar-valued polynomial run from the (m, k) copy written by
+    # ipx_ppoly_pack_*; short calls read the reference's (k, m) layout: same bits either way
+    g = np.random.default_rng(11)
+    m, k = 257, 5
+    x = np.sort(g.uniform(-1, 1, m + 1))
+    c = g.normal(size=(k, m))
+    xq = g.uniform(-1.2, 1.2, 8 * m)
+    p = ipx.PPoly(c, x)
+    for nu in (0, 1, 3):
+        whole = p(xq, nu)                                  # >= 4 m queries: piece-major
+        parts = np.concatenate([p(xq[i:i + m], nu) for i in range(0, xq.size, m)])  # (k, m) layout
+        assert np.array_equal(whole, parts)
+    assert "_packed" in p.__dict__
