@@ -21,7 +21,7 @@ HEADERS = [os.path.join(CSRC, "ipx_device.cuh"), os.path.join(CSRC, "ipx_eval_ti
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-shared", "--threads", "6",
 ]
 
 

@@ -172,9 +172,11 @@ def load() -> C.CDLL:
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB
-    if _build.is_stale() and _build.find_nvcc() is not None:
-        _build.build()
+    path = os.environ.get("IPX_LIB")  # experiments: another build of the same sources
+    if path is None:
+        path = _build.LIB
+        if _build.is_stale() and _build.find_nvcc() is not None:
+            _build.build()
     if not os.path.exists(path):
         raise ImportError(
             f"{path} is missing and nvcc is not available to build it: the interpax_b200 "

@@ -39,14 +39,17 @@ constexpr int kMaxGroups = 4;       // more distinct columns than this in a warp
 constexpr int kSmemKnotCap = 6144;  // total knots (all axes) staged in shared memory
 
 // RC = nodes of one run held per column (16: dense queries, several per cell; 32: sparse ones)
-template <typename T, int ND, int RC = 16> struct TileCfg {
+template <typename T, int ND, int RC = 16, int QPL = 2> struct TileCfg {
   static constexpr int NT = 1 << ND;                       // values per record
   static constexpr int NC = 1 << (ND - 1);                 // columns per group
   static constexpr int NCA = ND > 1 ? ND - 1 : 1;          // column axes (array extent)
   static constexpr int REC_BYTES = NT * (int)sizeof(T);
   static constexpr int CH = REC_BYTES / 16;                // 16-byte chunks per record
   static constexpr int STRIDE = REC_BYTES + (REC_BYTES >= 32 ? 16 : 0);  // bank-conflict padding
-  static constexpr int WARP_TILE_BYTES = NC * RC * STRIDE;
+  static constexpr int RUN_BYTES = NC * RC * STRIDE;         // node runs of one group
+  static constexpr int QSLOT = QPL * (int)sizeof(T);         // a lane's coordinates on one axis
+  static constexpr int QAXIS = 32 * QSLOT;
+  static constexpr int WARP_TILE_BYTES = RUN_BYTES + ((ND * QAXIS + 15) & ~15);  // + next round's queries
 };
 
 // rare paths kept out of line (values in and out through registers only): the hot loop must
@@ -84,8 +87,17 @@ __device__ __forceinline__ void hermite_weights_r(T q, T x0, T x1, int order, T 
 }
 
 // table index of knot position p along the LAST axis (run axis)
-template <typename T> __device__ __forceinline__ int run_table_index(const AxisDesc<T>& A, int p) {
-  return padded_to_table(A, p);
+template <typename T, int WM, int AX>
+__device__ __forceinline__ int run_table_index(const AxisDesc<T>& A, int p) {
+  if constexpr (WM >= 0) {
+    if constexpr (((WM >> AX) & 1) == 0) return p;
+    int s = p - 1;
+    if (s < 0) s += A.n;
+    if (s >= A.n) s -= A.n;
+    return s;
+  } else {
+    return padded_to_table(A, p);
+  }
 }
 
 // knot-derived constants of one axis (need device data, so they live in shared memory);
@@ -106,6 +118,15 @@ template <typename T, int ND> struct QState {
 __device__ __forceinline__ void cp_async16_s(unsigned smem_dst, const void* gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 }
+template <int BYTES> __device__ __forceinline__ void cp_async_s(unsigned smem_dst, const void* gmem_src) {
+  if constexpr (BYTES == 16) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+  } else if constexpr (BYTES == 8) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+  } else {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+  }
+}
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.wait_all;\n" ::: "memory");
 }
@@ -115,11 +136,20 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // TWO: two consecutive queries per lane (dense streams, several queries per cell: the pair
 // shares node layers); otherwise one per lane (sparse streams, about one query per cell or
 // fewer: a warp's queries then span fewer cells, fit one run and keep every lane busy).
-template <typename T, int ND, bool DEVP, bool ORD0, int RC, bool TWO = true>
+// WM: -1, or the set of periodic axes as a compile-time mask (bit ax).  The mask form is used
+// when every periodic axis wraps its queries and maps padded positions to the table without a
+// permutation (sorted knots, un-padded tables: what Interpolator1D/2D/3D passes); the wrap,
+// seam and fill code of the other axes then drops out of the loop instead of being branched
+// around per query.
+template <typename T, int ND, bool DEVP, bool ORD0, int RC, bool TWO = true, int WM = -1>
 __global__ void __launch_bounds__(kTileThreads, sizeof(T) == 4 ? 3 : 2)
 eval_tile_kernel(const EvalArgs<T, ND> a) {
   constexpr int QPL = TWO ? 2 : 1;  // queries per lane per round
-  using Cfg = TileCfg<T, ND, RC>;
+  using Cfg = TileCfg<T, ND, RC, QPL>;
+  constexpr bool CTM = WM >= 0;
+#define IPXT_WRAP(AXI) (CTM ? (((WM >> (AXI)) & 1) != 0) : (a.ax[AXI].wrap != 0))
+#define IPXT_PERIODIC(AXI) (CTM ? (((WM >> (AXI)) & 1) != 0) : (a.ax[AXI].periodic != 0))
+#define IPXT_PERM(AXI) (CTM ? (const int32_t*)nullptr : a.ax[AXI].perm)
   constexpr int kRunCap = RC;
   constexpr int LPC = 32 / Cfg::NC;          // lanes that copy one column
   constexpr int NPR = LPC / Cfg::CH;         // nodes of a column copied per round
@@ -159,7 +189,7 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
   const AxisDesc<T>& RA = a.ax[ND - 1];  // run axis
   // the run of nodes is contiguous in the table unless the run axis is periodic with a
   // permutation (un-sorted knots) or the run crosses the periodic seam
-  const bool run_identity = !RA.periodic || RA.perm == nullptr;
+  const bool run_identity = !IPXT_PERIODIC(ND - 1) || IPXT_PERM(ND - 1) == nullptr;
   const bool want_idx = a.idx_out != nullptr;
 
   // this lane's role in the cooperative copy: column `ccol`, chunk `lane % LPC` of each round
@@ -170,78 +200,14 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
   const unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);
   const unsigned cdst0 = tile_s + (ccol * kRunCap + cnode0) * Cfg::STRIDE + 16 * cpart;
 
-  // ---- one located query -------------------------------------------------------------
-  // `cell` carries the located interval of the lane's first query ({x0, x1, 1/dx} per axis) to
-  // its second one: neighbours in a sorted stream are usually in the same interval, and then
-  // two comparisons replace the search (the result is the same interval by definition).
-  auto locate_q = [&](const T (&qraw)[ND], QState<T, ND>& S, int& pz, T (&cell)[ND][3],
-                      const QState<T, ND>* first) {
-    S.fill = 0;
-#pragma unroll
-    for (int ax = 0; ax < ND; ++ax) {
-      const AxisDesc<T>& A = a.ax[ax];
-      T q = qraw[ax];
-      if (A.wrap) {
-        const T Pd = T(fabs(P.axis[ax].period));
-        // [-P,0): fmod leaves q and the sign fix adds P;  [P,2P): q - P is exact (Sterbenz);
-        // anything that does not land in [0,P) takes the exact remainder
-        T r = q < T(0) ? q + Pd : (q >= Pd ? q - Pd : q);
-        if (!(r >= T(0) && r < Pd)) r = py_mod_slow(q, Pd);
-        q = r;
-      }
-      const int nk = A.nk;
-      int koff = 0;
-#pragma unroll
-      for (int k = 0; k < ax; ++k) koff += 2 * a.ax[k].nk;
-      const T* ks = smT + koff;
-      const T xf = AX[ax].x_first;
-      int i;
-      T lo, hi, dxi;
-      if (first != nullptr && q >= cell[ax][0] && q < cell[ax][1]) {
-        i = first->li[ax]; lo = cell[ax][0]; hi = cell[ax][1]; dxi = cell[ax][2];
-      } else {
-        const T ih = AX[ax].inv_h;
-        i = min(max(t_floor_to_int((q - xf) * ih), 0), nk - 2) + 1;
-        lo = ks[i - 1]; hi = ks[i];
-        // exact check of the guess against the knots (NaN fails it); the rare miss re-searches
-        if (!((q >= lo || i == 1) && (q < hi || i == nk - 1))) {
-          i = bin_index_slow(ks, nk, q, xf, ih);
-          lo = ks[i - 1];
-          hi = ks[i];
-        }
-        dxi = ks[nk + i];
-      }
-      if (first == nullptr) { cell[ax][0] = lo; cell[ax][1] = hi; cell[ax][2] = dxi; }
-      S.li[ax] = i;
-      hermite_weights_r<T, ORD0>(q, lo, hi, P.axis[ax].derivative, dxi, S.w[ax]);
-      if (!A.wrap) {
-        const ipx_axis_params& pa = P.axis[ax];
-        if (!pa.keep_lo && q < xf) S.fill |= 1u << (2 * ax);
-        if (!pa.keep_hi && q > AX[ax].x_last) S.fill |= 2u << (2 * ax);
-      }
-      if (ax < ND - 1) {
-        if (A.periodic) {
-          int s0 = i - 2; s0 += s0 < 0 ? A.n : 0;
-          int s1 = i - 1; s1 -= s1 >= A.n ? A.n : 0;
-          const int32_t* pm = A.perm;
-          S.t0[ax] = pm ? pm[s0] : s0;
-          S.t1[ax] = pm ? pm[s1] : s1;
-        } else {
-          S.t0[ax] = i - 1; S.t1[ax] = i;
-        }
-      }
-    }
-    pz = S.li[ND - 1] - 1;
-  };
-
   // ---- locate both queries of the lane ---------------------------------------------------
   // Written as three straight-line phases so that the 2 x ND independent dependency chains
   // (wrap -> guess -> knot loads -> check -> weights) interleave instead of running one after
   // the other: (A) wrap, guess and knot loads for every (query, axis) with the exceptional
   // cases only FLAGGED; (B) one branch that repairs flagged entries (rare: |q| beyond one
   // period, a guess off by a cell, NaN); (C) weights, fill flags and corner indices.
-  // Used in 1-D / 2-D; in 3-D holding all chains at once exceeds the 128-register budget and
-  // the sequential locate_q above (with interval reuse for the second query) is faster.
+  // The next round's coordinates wait in shared memory, not in registers (see the loop below),
+  // which is what lets the 2 x 3 chains of a 3-D pair fit the 128-register budget.
   auto locate_range = [&](const T (&qraw)[2][ND], QState<T, ND> (&S)[2], int (&pz)[2], const int k_lo,
                           const int k_hi) {
     T q[2][ND], lo[2][ND], hi[2][ND], dxi[2][ND];
@@ -264,8 +230,8 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
         T v = qraw[k][ax];
         // [-P,0): fmod leaves q and the sign fix adds P;  [P,2P): q - P is exact (Sterbenz)
         const T r = v < T(0) ? v + Pd : (v >= Pd ? v - Pd : v);
-        const bool wrap_bad = A.wrap && !(r >= T(0) && r < Pd);
-        v = A.wrap ? r : v;
+        const bool wrap_bad = IPXT_WRAP(ax) && !(r >= T(0) && r < Pd);
+        v = IPXT_WRAP(ax) ? r : v;
         const int i = min(max(t_floor_to_int((v - xf) * ih), 0), nk - 2) + 1;
         const T l = ks[i - 1], h = ks[i];
         // exact check of the guess against the knots; NaN fails it
@@ -290,7 +256,7 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
           if (k < k_lo || k >= k_hi) continue;
           if (bad & (1u << (2 * ax + k))) {
             T v = qraw[k][ax];
-            if (A.wrap) v = py_mod_slow(v, T(fabs(P.axis[ax].period)));
+            if (IPXT_WRAP(ax)) v = py_mod_slow(v, T(fabs(P.axis[ax].period)));
             const int i = bin_index_slow(ks, nk, v, AX[ax].x_first, AX[ax].inv_h);
             q[k][ax] = v; ii[k][ax] = i;
             lo[k][ax] = ks[i - 1]; hi[k][ax] = ks[i]; dxi[k][ax] = ks[nk + i];
@@ -311,15 +277,15 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
         hermite_weights_r<T, ORD0>(q[k][ax], lo[k][ax], hi[k][ax], P.axis[ax].derivative, dxi[k][ax],
                                    S[k].w[ax]);
         const ipx_axis_params& pa = P.axis[ax];
-        const bool flo = !A.wrap && !pa.keep_lo && q[k][ax] < AX[ax].x_first;
-        const bool fhi = !A.wrap && !pa.keep_hi && q[k][ax] > AX[ax].x_last;
+        const bool flo = !IPXT_WRAP(ax) && !pa.keep_lo && q[k][ax] < AX[ax].x_first;
+        const bool fhi = !IPXT_WRAP(ax) && !pa.keep_hi && q[k][ax] > AX[ax].x_last;
         S[k].fill |= (flo ? 1u : 0u) << (2 * ax);
         S[k].fill |= (fhi ? 2u : 0u) << (2 * ax);
         if (ax < ND - 1) {
           int s0 = i - 2; s0 += s0 < 0 ? A.n : 0;
           int s1 = i - 1; s1 -= s1 >= A.n ? A.n : 0;
-          S[k].t0[ax] = A.periodic ? s0 : i - 1;
-          S[k].t1[ax] = A.periodic ? s1 : i;
+          S[k].t0[ax] = IPXT_PERIODIC(ax) ? s0 : i - 1;
+          S[k].t1[ax] = IPXT_PERIODIC(ax) ? s1 : i;
         }
       }
       pz[k] = S[k].li[ND - 1] - 1;
@@ -327,7 +293,7 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
     // un-sorted periodic knots: sorted position -> table index (rare; identity is passed as NULL)
 #pragma unroll
     for (int ax = 0; ax < ND - 1; ++ax) {
-      const int32_t* pm = a.ax[ax].periodic ? a.ax[ax].perm : nullptr;
+      const int32_t* pm = IPXT_PERIODIC(ax) ? IPXT_PERM(ax) : nullptr;
       if (pm != nullptr) {
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
@@ -362,7 +328,7 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
     W.w[0] = S.w;
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk) {
-      const int zt = run_table_index(RA, pz + kk);
+      const int zt = run_table_index<T, WM, ND - 1>(RA, pz + kk);
       T A[1][2];
       layer_contract<T, ND, 1>(
           [&](int c, T* r) {
@@ -401,24 +367,21 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
   const int rounds = (int)((a.nq - w0 + step - 1) / step);
 
   int64_t qa = w0 + QPL * lane;  // this lane's first query; its second (TWO) is qa + 1
-  T qn[2][ND];
+  // The coordinates of the next round travel global -> shared with cp.async into the lane's own
+  // slots (QSLOT bytes per axis) and are read back at the top of that round, so they cost no
+  // registers while the current round runs.  Each lane reads its slots before it issues the
+  // copy that overwrites them, and nobody else touches them: no warp synchronisation needed.
+  char* const qslot = tile + Cfg::RUN_BYTES + Cfg::QSLOT * lane;
+  const unsigned qslot_s = (unsigned)__cvta_generic_to_shared(qslot);
   auto prefetch = [&](int64_t q) {
 #pragma unroll
     for (int ax = 0; ax < ND; ++ax) {
-      if constexpr (!TWO) {
-        qn[0][ax] = q < a.nq ? __ldcs(a.ax[ax].q + q) : T(0);
-        qn[1][ax] = T(0);
-      } else if (q + 1 < a.nq) {  // q is even and the arrays are 16-byte aligned: one vector load
-        if (sizeof(T) == 8) {
-          const double2 v = __ldcs(reinterpret_cast<const double2*>(a.ax[ax].q + q));
-          qn[0][ax] = T(v.x); qn[1][ax] = T(v.y);
-        } else {
-          const float2 v = __ldcs(reinterpret_cast<const float2*>(a.ax[ax].q + q));
-          qn[0][ax] = T(v.x); qn[1][ax] = T(v.y);
-        }
+      if (q + QPL - 1 < a.nq) {  // q is a multiple of QPL and the arrays are 16-byte aligned
+        cp_async_s<Cfg::QSLOT>(qslot_s + ax * Cfg::QAXIS, a.ax[ax].q + q);
       } else {
-        qn[0][ax] = q < a.nq ? a.ax[ax].q[q] : T(0);
-        qn[1][ax] = T(0);
+        T* d = reinterpret_cast<T*>(qslot + ax * Cfg::QAXIS);
+        d[0] = q < a.nq ? a.ax[ax].q[q] : T(0);
+        if constexpr (TWO) d[1] = T(0);
       }
     }
   };
@@ -428,21 +391,27 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
     const bool act_a = qa < a.nq;
     const bool act_b = TWO && qa + 1 < a.nq;
     T qc[2][ND];
+    cp_async_wait_all();
 #pragma unroll
-    for (int k = 0; k < 2; ++k)
-#pragma unroll
-      for (int ax = 0; ax < ND; ++ax) qc[k][ax] = qn[k][ax];
+    for (int ax = 0; ax < ND; ++ax) {
+      const T* v = reinterpret_cast<const T*>(qslot + ax * Cfg::QAXIS);
+      if constexpr (TWO) {
+        if constexpr (sizeof(T) == 8) {
+          const double2 w = *reinterpret_cast<const double2*>(v);
+          qc[0][ax] = T(w.x); qc[1][ax] = T(w.y);
+        } else {
+          const float2 w = *reinterpret_cast<const float2*>(v);
+          qc[0][ax] = T(w.x); qc[1][ax] = T(w.y);
+        }
+      } else {
+        qc[0][ax] = v[0]; qc[1][ax] = T(0);
+      }
+    }
     if (round + 1 < rounds) prefetch(qa + step);
 
     QState<T, ND> SS[2];
     int pzz[2];
-    if constexpr (ND == 3) {
-      T cell[ND][3];
-      locate_q(qc[0], SS[0], pzz[0], cell, nullptr);
-      if constexpr (TWO) locate_q(qc[1], SS[1], pzz[1], cell, &SS[0]);
-    } else {
-      locate_range(qc, SS, pzz, 0, QPL);
-    }
+    locate_range(qc, SS, pzz, 0, QPL);
     if constexpr (!TWO) { SS[1] = SS[0]; pzz[1] = pzz[0]; }
     QState<T, ND>& Sa = SS[0];
     QState<T, ND>& Sb = SS[1];
@@ -486,7 +455,7 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
         // table position of the first node of the run, if the run is contiguous in the table
         int zt0 = zmin;
         bool contiguous = run_identity;
-        if (RA.periodic) {
+        if (IPXT_PERIODIC(ND - 1)) {
           zt0 = zmin - 1;
           contiguous = contiguous && zmin >= 1 && (zmin + extent - 1) <= RA.n;
         }
@@ -501,7 +470,7 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
           }
         } else {
           for (int node = cnode0; node < extent; node += NPR) {
-            const int zt = run_table_index(RA, zmin + node);
+            const int zt = run_table_index<T, WM, ND - 1>(RA, zmin + node);
             cp_async16_s(tile_s + (ccol * kRunCap + node) * Cfg::STRIDE + 16 * cpart,
                          tabc + ((size_t)colnode * RA.n + zt) * Cfg::REC_BYTES + 16 * cpart);
           }
@@ -557,21 +526,24 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
     if (act_a) store_q(Sa, qa, res_a);
     if (act_b) store_q(Sb, qa + 1, res_b);
   }
+#undef IPXT_WRAP
+#undef IPXT_PERIODIC
+#undef IPXT_PERM
 }
 
 // dynamic shared memory the tile kernel needs
-template <typename T, int ND, int RC> static size_t tile_smem_bytes(const EvalArgs<T, ND>& a) {
+template <typename T, int ND, int RC, int QPL = 2> static size_t tile_smem_bytes(const EvalArgs<T, ND>& a) {
   size_t knots = 0;
   for (int ax = 0; ax < ND; ++ax) knots += 2 * (size_t)a.ax[ax].nk * sizeof(T);
   knots = (knots + 15) & ~(size_t)15;
-  return knots + (size_t)kTileWarps * TileCfg<T, ND, RC>::WARP_TILE_BYTES;
+  return knots + (size_t)kTileWarps * TileCfg<T, ND, RC, QPL>::WARP_TILE_BYTES;
 }
 
 template <typename T, int ND, int RC> static int tile_ctas_per_sm_query(size_t smem);
 
 // resident CTAs per SM for a run capacity (register- or shared-memory-bound)
-template <typename T, int ND, int RC> static int tile_ctas_per_sm(const EvalArgs<T, ND>& a) {
-  const size_t smem = tile_smem_bytes<T, ND, RC>(a);
+template <typename T, int ND, int RC, int QPL> static int tile_ctas_per_sm(const EvalArgs<T, ND>& a) {
+  const size_t smem = tile_smem_bytes<T, ND, RC, QPL>(a);
   // the answer depends on the shared-memory size only; remember the last one, size and
   // answer packed in one atomic word so concurrent callers never see a mixed pair
   static std::atomic<unsigned long long> last{~0ull};
@@ -583,7 +555,7 @@ template <typename T, int ND, int RC> static int tile_ctas_per_sm(const EvalArgs
 }
 
 template <typename T, int ND, int RC> static int tile_ctas_per_sm_query(size_t smem) {
-  auto kern = eval_tile_kernel<T, ND, false, true, RC, true>;
+  auto kern = eval_tile_kernel<T, ND, false, true, RC, true, -1>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return 0;
   int per_sm = 0;
@@ -594,15 +566,21 @@ template <typename T, int ND, int RC> static int tile_ctas_per_sm_query(size_t s
   return per_sm;
 }
 
-template <typename T, int ND, int RC, bool TWO = true>
-static bool launch_tile_rc(const EvalArgs<T, ND>& a, cudaStream_t s) {
+template <typename T, int ND, int RC, bool TWO, int WM>
+static bool launch_tile_wm(const EvalArgs<T, ND>& a, cudaStream_t s) {
   constexpr int QPL = TWO ? 2 : 1;
-  const size_t smem = tile_smem_bytes<T, ND, RC>(a);
+  const size_t smem = tile_smem_bytes<T, ND, RC, QPL>(a);
   bool ord0 = a.dp == nullptr;
   for (int ax = 0; ax < ND && ord0; ++ax) ord0 = a.hp.axis[ax].derivative <= 0;
-  auto kern = a.dp ? eval_tile_kernel<T, ND, true, false, RC, TWO>
-                   : (ord0 ? eval_tile_kernel<T, ND, false, true, RC, TWO>
-                           : eval_tile_kernel<T, ND, false, false, RC, TWO>);
+  void (*kern)(const EvalArgs<T, ND>);
+  if constexpr (WM >= 0) {
+    kern = ord0 ? eval_tile_kernel<T, ND, false, true, RC, TWO, WM>
+                : eval_tile_kernel<T, ND, false, false, RC, TWO, WM>;
+  } else {
+    kern = a.dp ? eval_tile_kernel<T, ND, true, false, RC, TWO, -1>
+                : (ord0 ? eval_tile_kernel<T, ND, false, true, RC, TWO, -1>
+                        : eval_tile_kernel<T, ND, false, false, RC, TWO, -1>);
+  }
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return false;
   int dev = 0, sms = 148, per_sm = 1;
@@ -615,6 +593,28 @@ static bool launch_tile_rc(const EvalArgs<T, ND>& a, cudaStream_t s) {
   if (need < grid) grid = need;
   kern<<<(int)grid, kTileThreads, smem, s>>>(a);
   return true;
+}
+
+// The periodic axes as a compile-time mask when the call allows it (host-resident operands,
+// no knot permutation, un-padded tables) and the mask is one of the common ones: none, all,
+// or all but the last axis.  Anything else runs the kernel that reads the flags per query.
+template <typename T, int ND, int RC, bool TWO = true>
+static bool launch_tile_rc(const EvalArgs<T, ND>& a, cudaStream_t s) {
+  int mask = 0;
+  bool ct = a.dp == nullptr && getenv("IPX_TILE_RUNTIME_FLAGS") == nullptr;
+  for (int ax = 0; ax < ND; ++ax) {
+    const AxisDesc<T>& A = a.ax[ax];
+    ct = ct && A.perm == nullptr && (A.periodic != 0) == (A.wrap != 0);
+    mask |= (A.wrap != 0) << ax;
+  }
+  constexpr int ALL = (1 << ND) - 1;
+  constexpr int HEAD = (1 << (ND - 1)) - 1;  // every axis but the last
+  if (ct && mask == 0) return launch_tile_wm<T, ND, RC, TWO, 0>(a, s);
+  if (ct && mask == ALL) return launch_tile_wm<T, ND, RC, TWO, ALL>(a, s);
+  if constexpr (ND > 1) {
+    if (ct && mask == HEAD) return launch_tile_wm<T, ND, RC, TWO, HEAD>(a, s);
+  }
+  return launch_tile_wm<T, ND, RC, TWO, -1>(a, s);
 }
 
 // true if (T, ND) has a tile kernel: records of at least 16 bytes
@@ -646,8 +646,10 @@ static bool launch_tile(const EvalArgs<T, ND>& a, cudaStream_t s) {
     double cells = 1.0;
     for (int ax = 0; ax < ND; ++ax) cells *= (double)(a.ax[ax].n > 1 ? a.ax[ax].n - 1 : 1);
     const bool two = (double)a.nq >= 3.0 * cells;
-    const bool long_run = (double)a.nq < 5.0 * cells &&
-                          tile_ctas_per_sm<T, ND, 32>(a) >= tile_ctas_per_sm<T, ND, 16>(a);
+    const bool long_run =
+        (double)a.nq < 5.0 * cells &&
+        (two ? tile_ctas_per_sm<T, ND, 32, 2>(a) >= tile_ctas_per_sm<T, ND, 16, 2>(a)
+             : tile_ctas_per_sm<T, ND, 32, 1>(a) >= tile_ctas_per_sm<T, ND, 16, 1>(a));
     const char* e = getenv("IPX_TILE_MODE");  // experiment switch (profiles/sweep_tile_modes.sh)
     if (e != nullptr) {
       if (e[0] == 'a') return launch_tile_rc<T, ND, 16, true>(a, s);
