@@ -374,11 +374,12 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
   char* const qslot = tile + Cfg::RUN_BYTES + Cfg::QSLOT * lane;
   const unsigned qslot_s = (unsigned)__cvta_generic_to_shared(qslot);
   auto prefetch = [&](int64_t q) {
+    if (q + QPL - 1 < a.nq) {  // q is a multiple of QPL and the arrays are 16-byte aligned
 #pragma unroll
-    for (int ax = 0; ax < ND; ++ax) {
-      if (q + QPL - 1 < a.nq) {  // q is a multiple of QPL and the arrays are 16-byte aligned
-        cp_async_s<Cfg::QSLOT>(qslot_s + ax * Cfg::QAXIS, a.ax[ax].q + q);
-      } else {
+      for (int ax = 0; ax < ND; ++ax) cp_async_s<Cfg::QSLOT>(qslot_s + ax * Cfg::QAXIS, a.ax[ax].q + q);
+    } else {
+#pragma unroll
+      for (int ax = 0; ax < ND; ++ax) {
         T* d = reinterpret_cast<T*>(qslot + ax * Cfg::QAXIS);
         d[0] = q < a.nq ? a.ax[ax].q[q] : T(0);
         if constexpr (TWO) d[1] = T(0);
