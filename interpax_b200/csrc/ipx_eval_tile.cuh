@@ -33,8 +33,12 @@
 
 namespace ipx {
 
-constexpr int kTileThreads = 256;
-constexpr int kTileWarps = kTileThreads / 32;
+// One CTA per SM: the knot vectors (and their reciprocal widths) are staged once per SM, not once
+// per resident CTA, and what shared memory is not needed stays L1 -- the direct gathers of
+// incoherent (random-order) streams live on L1 capacity.  The register file holds 16 warps of a
+// float64 kernel (128 registers) or 24 of a float32 one (80); the launch uses fewer warps when
+// long knot vectors leave less room for the per-warp tiles.
+template <typename T> constexpr int tile_max_threads() { return sizeof(T) == 4 ? 768 : 512; }
 constexpr int kMaxGroups = 4;       // more distinct columns than this in a warp -> direct path
 constexpr int kSmemKnotCap = 6144;  // total knots (all axes) staged in shared memory
 
@@ -118,13 +122,21 @@ template <typename T, int ND> struct QState {
 __device__ __forceinline__ void cp_async16_s(unsigned smem_dst, const void* gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 }
-template <int BYTES> __device__ __forceinline__ void cp_async_s(unsigned smem_dst, const void* gmem_src) {
+// query coordinates are read once: evict-first in L2, so the stream does not push table lines out
+// (the register path used __ldcs for the same reason)
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+  return pol;
+}
+template <int BYTES>
+__device__ __forceinline__ void cp_async_s(unsigned smem_dst, const void* gmem_src, unsigned long long pol) {
   if constexpr (BYTES == 16) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(smem_dst), "l"(gmem_src), "l"(pol) : "memory");
   } else if constexpr (BYTES == 8) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;\n" ::"r"(smem_dst), "l"(gmem_src), "l"(pol) : "memory");
   } else {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;\n" ::"r"(smem_dst), "l"(gmem_src), "l"(pol) : "memory");
   }
 }
 __device__ __forceinline__ void cp_async_wait_all() {
@@ -142,7 +154,7 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // seam and fill code of the other axes then drops out of the loop instead of being branched
 // around per query.
 template <typename T, int ND, bool DEVP, bool ORD0, int RC, bool TWO = true, int WM = -1>
-__global__ void __launch_bounds__(kTileThreads, sizeof(T) == 4 ? 3 : 2)
+__global__ void __launch_bounds__(tile_max_threads<T>(), 1)
 eval_tile_kernel(const EvalArgs<T, ND> a) {
   constexpr int QPL = TWO ? 2 : 1;  // queries per lane per round
   using Cfg = TileCfg<T, ND, RC, QPL>;
@@ -172,7 +184,7 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
 #pragma unroll
   for (int ax = 0; ax < ND; ++ax) {
     const int nk = a.ax[ax].nk;
-    for (int i = threadIdx.x; i < nk; i += kTileThreads) {
+    for (int i = threadIdx.x; i < nk; i += (int)blockDim.x) {
       T xi = a.ax[ax].knots[i];
       smT[knot_elems + i] = xi;
       smT[knot_elems + nk + i] = i > 0 ? safe_recip(xi - a.ax[ax].knots[i - 1]) : T(0);
@@ -361,8 +373,8 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
   };
 
   // ---- persistent loop: 64 consecutive queries per warp per round ------------------------
-  const int64_t step = (int64_t)gridDim.x * kTileThreads * QPL;
-  const int64_t w0 = ((int64_t)blockIdx.x * kTileWarps + warp) * (32 * QPL);  // warp's first query
+  const int64_t step = (int64_t)gridDim.x * blockDim.x * QPL;
+  const int64_t w0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) * (32 * QPL);  // warp's first query
   if (w0 >= a.nq) return;  // whole warp idle (after the CTA barrier above)
   const int rounds = (int)((a.nq - w0 + step - 1) / step);
 
@@ -375,8 +387,10 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
   const unsigned qslot_s = (unsigned)__cvta_generic_to_shared(qslot);
   auto prefetch = [&](int64_t q) {
     if (q + QPL - 1 < a.nq) {  // q is a multiple of QPL and the arrays are 16-byte aligned
+      const unsigned long long pol = l2_evict_first_policy();
 #pragma unroll
-      for (int ax = 0; ax < ND; ++ax) cp_async_s<Cfg::QSLOT>(qslot_s + ax * Cfg::QAXIS, a.ax[ax].q + q);
+      for (int ax = 0; ax < ND; ++ax)
+        cp_async_s<Cfg::QSLOT>(qslot_s + ax * Cfg::QAXIS, a.ax[ax].q + q, pol);
     } else {
 #pragma unroll
       for (int ax = 0; ax < ND; ++ax) {
@@ -532,45 +546,37 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
 #undef IPXT_PERM
 }
 
-// dynamic shared memory the tile kernel needs
-template <typename T, int ND, int RC, int QPL = 2> static size_t tile_smem_bytes(const EvalArgs<T, ND>& a) {
+// shared memory of the staged knots and reciprocal widths
+template <typename T, int ND> static size_t tile_knot_bytes(const EvalArgs<T, ND>& a) {
   size_t knots = 0;
   for (int ax = 0; ax < ND; ++ax) knots += 2 * (size_t)a.ax[ax].nk * sizeof(T);
-  knots = (knots + 15) & ~(size_t)15;
-  return knots + (size_t)kTileWarps * TileCfg<T, ND, RC, QPL>::WARP_TILE_BYTES;
+  return (knots + 15) & ~(size_t)15;
 }
 
-template <typename T, int ND, int RC> static int tile_ctas_per_sm_query(size_t smem);
-
-// resident CTAs per SM for a run capacity (register- or shared-memory-bound)
-template <typename T, int ND, int RC, int QPL> static int tile_ctas_per_sm(const EvalArgs<T, ND>& a) {
-  const size_t smem = tile_smem_bytes<T, ND, RC, QPL>(a);
-  // the answer depends on the shared-memory size only; remember the last one, size and
-  // answer packed in one atomic word so concurrent callers never see a mixed pair
-  static std::atomic<unsigned long long> last{~0ull};
-  const unsigned long long seen = last.load(std::memory_order_relaxed);
-  if ((seen >> 8) == (unsigned long long)smem) return (int)(seen & 0xff);
-  const int ctas = tile_ctas_per_sm_query<T, ND, RC>(smem);
-  last.store(((unsigned long long)smem << 8) | (unsigned)(ctas & 0xff), std::memory_order_relaxed);
-  return ctas;
-}
-
-template <typename T, int ND, int RC> static int tile_ctas_per_sm_query(size_t smem) {
-  auto kern = eval_tile_kernel<T, ND, false, true, RC, true, -1>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-    return 0;
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, smem) != cudaSuccess) {
-    cudaGetLastError();
-    return 0;
+// warps of one CTA: as many as the register file holds, fewer if the shared memory left beside
+// the knots does not hold that many per-warp tiles
+template <typename T, int ND, int RC, int QPL> static int tile_warps(const EvalArgs<T, ND>& a) {
+  static std::atomic<int> optin{0};  // opt-in shared memory per block of the current device
+  int lim = optin.load(std::memory_order_relaxed);
+  if (lim == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || lim <= 0)
+      lim = 48 * 1024;
+    optin.store(lim, std::memory_order_relaxed);
   }
-  return per_sm;
+  const long long room = (long long)lim - 1024 - (long long)tile_knot_bytes<T, ND>(a);  // 1 KB: static
+  const long long fit = room / TileCfg<T, ND, RC, QPL>::WARP_TILE_BYTES;
+  const int maxw = tile_max_threads<T>() / 32;
+  return fit >= maxw ? maxw : (fit < 0 ? 0 : (int)fit);
 }
 
 template <typename T, int ND, int RC, bool TWO, int WM>
 static bool launch_tile_wm(const EvalArgs<T, ND>& a, cudaStream_t s) {
   constexpr int QPL = TWO ? 2 : 1;
-  const size_t smem = tile_smem_bytes<T, ND, RC, QPL>(a);
+  const int warps = tile_warps<T, ND, RC, QPL>(a);
+  if (warps < 4) return false;  // the generic kernel serves such knot vectors
+  const size_t smem = tile_knot_bytes<T, ND>(a) + (size_t)warps * TileCfg<T, ND, RC, QPL>::WARP_TILE_BYTES;
   bool ord0 = a.dp == nullptr;
   for (int ax = 0; ax < ND && ord0; ++ax) ord0 = a.hp.axis[ax].derivative <= 0;
   void (*kern)(const EvalArgs<T, ND>);
@@ -584,15 +590,14 @@ static bool launch_tile_wm(const EvalArgs<T, ND>& a, cudaStream_t s) {
   }
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return false;
-  int dev = 0, sms = 148, per_sm = 1;
+  int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, smem);
-  if (per_sm < 1) per_sm = 1;
-  int64_t need = (a.nq + QPL * kTileThreads - 1) / (QPL * kTileThreads);
-  int64_t grid = (int64_t)sms * per_sm;  // persistent: one resident wave
+  const int threads = warps * 32;
+  int64_t need = (a.nq + QPL * threads - 1) / (QPL * threads);
+  int64_t grid = sms;  // persistent: one CTA per SM
   if (need < grid) grid = need;
-  kern<<<(int)grid, kTileThreads, smem, s>>>(a);
+  kern<<<(int)grid, threads, smem, s>>>(a);
   return true;
 }
 
@@ -649,8 +654,8 @@ static bool launch_tile(const EvalArgs<T, ND>& a, cudaStream_t s) {
     const bool two = (double)a.nq >= 3.0 * cells;
     const bool long_run =
         (double)a.nq < 5.0 * cells &&
-        (two ? tile_ctas_per_sm<T, ND, 32, 2>(a) >= tile_ctas_per_sm<T, ND, 16, 2>(a)
-             : tile_ctas_per_sm<T, ND, 32, 1>(a) >= tile_ctas_per_sm<T, ND, 16, 1>(a));
+        (two ? tile_warps<T, ND, 32, 2>(a) >= tile_warps<T, ND, 16, 2>(a)
+             : tile_warps<T, ND, 32, 1>(a) >= tile_warps<T, ND, 16, 1>(a));
     const char* e = getenv("IPX_TILE_MODE");  // experiment switch (profiles/sweep_tile_modes.sh)
     if (e != nullptr) {
       if (e[0] == 'a') return launch_tile_rc<T, ND, 16, true>(a, s);

@@ -946,3 +946,34 @@ def test_full_size_properties_f32_3d():
     up = lambda v: v.astype(np.float64)
     truth = O.Interpolator3D(up(xn), up(xn), up(zn), up(fn), "cubic", extrap, period)(*[up(v) for v in qn])
     assert_parity(r[:m].cpu().numpy(), want, "f32 3-D", truth)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_long_knot_vectors_shrink_the_cta(dtype):
+    """5000 x 24 x 40 nodes: the staged knots take most of the shared memory, so the tile
+    kernel runs with fewer warps per CTA (sparse stream: long runs, one query per lane) -- and
+    a denser, cell-sorted stream on the same table takes the two-per-lane shape.  Parity with
+    the oracle and bitwise agreement between the two orders."""
+    rng = np.random.default_rng(77)
+    nx, ny, nz = 5000, 24, 40
+    x = knots_nonuniform(rng, nx, 0.0, 50.0, dtype)
+    y = knots_nonuniform(rng, ny, -1.0, 1.0, dtype)
+    z = knots_nonuniform(rng, nz, 0.0, 3.0, dtype)
+    f = rng.normal(size=(nx, ny, nz)).astype(dtype)
+    ip = ipx.Interpolator3D(x, y, z, f, "cubic", extrap=True)
+    ref = O.Interpolator3D(x, y, z, f, "cubic", extrap=True)
+    for nq in (200_000, 20_000_000 if dtype == np.float64 else 2_000_000):
+        xq = rng.uniform(-0.1, 50.1, nq).astype(dtype)
+        yq = rng.uniform(-1.02, 1.02, nq).astype(dtype)
+        zq = rng.uniform(-0.05, 3.05, nq).astype(dtype)
+        key = ((np.searchsorted(x, xq) * ny + np.searchsorted(y, yq)) * nz + np.searchsorted(z, zq))
+        o = np.argsort(key, kind="stable")
+        r = ip(xq, yq, zq)
+        rs = ip(xq[o], yq[o], zq[o])
+        assert np.array_equal(rs, r[o])
+        m = 4096
+        assert_parity(rs[:m], ref(xq[o][:m], yq[o][:m], zq[o][:m]),
+                      truth=None if dtype == np.float64 else
+                      O.Interpolator3D(upcast(x), upcast(y), upcast(z), upcast(f), "cubic", extrap=True)(
+                          upcast(xq[o][:m]), upcast(yq[o][:m]), upcast(zq[o][:m])))
