@@ -36,9 +36,10 @@ namespace ipx {
 // One CTA per SM: the knot vectors (and their reciprocal widths) are staged once per SM, not once
 // per resident CTA, and what shared memory is not needed stays L1 -- the direct gathers of
 // incoherent (random-order) streams live on L1 capacity.  The register file holds 16 warps of a
-// float64 kernel (128 registers) or 24 of a float32 one (80); the launch uses fewer warps when
-// long knot vectors leave less room for the per-warp tiles.
-template <typename T> constexpr int tile_max_threads() { return sizeof(T) == 4 ? 768 : 512; }
+// float64 kernel (128 registers) or 20 of a float32 one (96; measured against 16 and 24 warps,
+// profiles/ in the DESIGN table); the launch uses fewer warps when long knot vectors leave less
+// room for the per-warp tiles.
+template <typename T> constexpr int tile_max_threads() { return sizeof(T) == 4 ? 640 : 512; }
 constexpr int kMaxGroups = 4;       // more distinct columns than this in a warp -> direct path
 constexpr int kSmemKnotCap = 6144;  // total knots (all axes) staged in shared memory
 
