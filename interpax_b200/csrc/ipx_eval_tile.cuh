@@ -39,7 +39,10 @@ namespace ipx {
 // float64 kernel (128 registers) or 20 of a float32 one (96; measured against 16 and 24 warps,
 // profiles/ in the DESIGN table); the launch uses fewer warps when long knot vectors leave less
 // room for the per-warp tiles.
-template <typename T> constexpr int tile_max_threads() { return sizeof(T) == 4 ? 640 : 512; }
+#ifndef IPX_TILE_F64_THREADS
+#define IPX_TILE_F64_THREADS 512
+#endif
+template <typename T> constexpr int tile_max_threads() { return sizeof(T) == 4 ? 640 : IPX_TILE_F64_THREADS; }
 constexpr int kMaxGroups = 4;       // more distinct columns than this in a warp -> direct path
 constexpr int kSmemKnotCap = 6144;  // total knots (all axes) staged in shared memory
 
@@ -64,6 +67,22 @@ template <typename T>
 __device__ __noinline__ int bin_index_slow(const T* x, int n, T q, T x_first, T inv_h) {
   T lo, hi;
   return bin_index(x, n, q, x_first, inv_h, lo, hi);
+}
+
+// One-period wrap of a query: r = q + P for q in [-P, 0), q - P for q in [P, 2P) (exact, Sterbenz),
+// q for q in [0, P) -- what the Python remainder gives there.  `bad` = anything else (|q| beyond one
+// period, NaN, -0.0, a sum that rounds up to P): the caller repairs those with the out-of-line
+// fmod.  Signs are tested on the integer pipe (q - P >= 0 <=> q >= P exactly), which leaves one
+// add and one compare on the FP64 pipe that bounds the kernel.
+__device__ __forceinline__ int sign_word(double v) { return __double2hiint(v); }
+__device__ __forceinline__ int sign_word(float v) { return __float_as_int(v); }
+template <typename T> __device__ __forceinline__ T wrap_one_period(T v, T Pd, bool& bad) {
+  const bool neg = sign_word(v) < 0;
+  const T s = v + (neg ? Pd : -Pd);
+  const bool s_neg = sign_word(s) < 0;
+  const T r = (neg || !s_neg) ? s : v;
+  bad = (neg && s_neg) || !(r < Pd);
+  return r;
 }
 
 // cubic Hermite weights from the local coordinate pieces (same formulas as hermite_weights)
@@ -241,10 +260,8 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
       for (int k = 0; k < 2; ++k) {
         if (k < k_lo || k >= k_hi) continue;
         T v = qraw[k][ax];
-        // [-P,0): fmod leaves q and the sign fix adds P;  [P,2P): q - P is exact (Sterbenz)
-        const T r = v < T(0) ? v + Pd : (v >= Pd ? v - Pd : v);
-        const bool wrap_bad = IPXT_WRAP(ax) && !(r >= T(0) && r < Pd);
-        v = IPXT_WRAP(ax) ? r : v;
+        bool wrap_bad = false;
+        if (IPXT_WRAP(ax)) v = wrap_one_period(v, Pd, wrap_bad);
         const int i = min(max(t_floor_to_int((v - xf) * ih), 0), nk - 2) + 1;
         const T l = ks[i - 1], h = ks[i];
         // exact check of the guess against the knots; NaN fails it
@@ -290,10 +307,13 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
         hermite_weights_r<T, ORD0>(q[k][ax], lo[k][ax], hi[k][ax], P.axis[ax].derivative, dxi[k][ax],
                                    S[k].w[ax]);
         const ipx_axis_params& pa = P.axis[ax];
-        const bool flo = !IPXT_WRAP(ax) && !pa.keep_lo && q[k][ax] < AX[ax].x_first;
-        const bool fhi = !IPXT_WRAP(ax) && !pa.keep_hi && q[k][ax] > AX[ax].x_last;
-        S[k].fill |= (flo ? 1u : 0u) << (2 * ax);
-        S[k].fill |= (fhi ? 2u : 0u) << (2 * ax);
+        // a query outside the knots sits in an end cell: the compares run only there
+        if (!IPXT_WRAP(ax) && (i == 1 || i == A.nk - 1)) {
+          const bool flo = !pa.keep_lo && q[k][ax] < AX[ax].x_first;
+          const bool fhi = !pa.keep_hi && q[k][ax] > AX[ax].x_last;
+          S[k].fill |= (flo ? 1u : 0u) << (2 * ax);
+          S[k].fill |= (fhi ? 2u : 0u) << (2 * ax);
+        }
         if (ax < ND - 1) {
           int s0 = i - 2; s0 += s0 < 0 ? A.n : 0;
           int s1 = i - 1; s1 -= s1 >= A.n ? A.n : 0;
@@ -318,14 +338,21 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
     }
   };
 
-  auto column_key = [&](const QState<T, ND>& S, bool& ok) {
-    unsigned key = 0;
+  // column key = interval indices of the column axes in mixed radix; it must stay below the
+  // "inactive lane" key 0xffffffff (checked once, the radices are uniform)
+  bool key_ok = true;
+  {
+    unsigned long long span = 1;
 #pragma unroll
     for (int ax = 0; ax < ND - 1; ++ax) {
-      const unsigned m = (unsigned)a.ax[ax].nk + 1u;
-      ok = ok && ((unsigned long long)key * m < 0xffff0000ull);
-      key = key * m + (unsigned)S.li[ax];
+      span *= (unsigned long long)a.ax[ax].nk + 1ull;
+      key_ok = key_ok && span < 0xffff0000ull;
     }
+  }
+  auto column_key = [&](const QState<T, ND>& S) {
+    unsigned key = 0;
+#pragma unroll
+    for (int ax = 0; ax < ND - 1; ++ax) key = key * ((unsigned)a.ax[ax].nk + 1u) + (unsigned)S.li[ax];
     return key;
   };
 
@@ -357,8 +384,8 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
     return res;
   };
 
-  auto store_q = [&](const QState<T, ND>& S, int64_t qi, T res) {
-    // extrapolation fills, x then y then z, later axes win (_spline.py:1101-1103)
+  // extrapolation fills, x then y then z, later axes win (_spline.py:1101-1103)
+  auto filled = [&](const QState<T, ND>& S, T res) {
     if (S.fill) {
 #pragma unroll
       for (int ax = 0; ax < ND; ++ax) {
@@ -366,11 +393,30 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
         if (S.fill & (2u << (2 * ax))) res = T(P.axis[ax].fill_hi);
       }
     }
-    __stcs(a.out + qi, res);
+    return res;
+  };
+  auto store_idx = [&](const QState<T, ND>& S, int64_t qi) {
     if (want_idx) {
 #pragma unroll
       for (int ax = 0; ax < ND; ++ax) a.idx_out[(int64_t)ax * a.nq + qi] = S.li[ax];
     }
+  };
+  auto store_q = [&](const QState<T, ND>& S, int64_t qi, T res) {
+    __stcs(a.out + qi, filled(S, res));
+    store_idx(S, qi);
+  };
+  // a lane's two results are adjacent: one store of the pair (qa is even; needs an aligned `out`)
+  const bool pair_store = TWO && (reinterpret_cast<uintptr_t>(a.out) & (2 * sizeof(T) - 1)) == 0;
+  auto store_pair = [&](const QState<T, ND>& S0, const QState<T, ND>& S1, int64_t qi, T r0, T r1) {
+    r0 = filled(S0, r0);
+    r1 = filled(S1, r1);
+    if constexpr (sizeof(T) == 8) {
+      __stcs(reinterpret_cast<double2*>(a.out + qi), make_double2(r0, r1));
+    } else {
+      __stcs(reinterpret_cast<float2*>(a.out + qi), make_float2(r0, r1));
+    }
+    store_idx(S0, qi);
+    store_idx(S1, qi + 1);
   };
 
   // ---- persistent loop: 64 consecutive queries per warp per round ------------------------
@@ -433,9 +479,8 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
     QState<T, ND>& Sb = SS[1];
     const int pza = pzz[0], pzb = pzz[1];
 
-    bool key_ok = true;
-    unsigned ka = column_key(Sa, key_ok);
-    const unsigned kb = column_key(Sb, key_ok);
+    unsigned ka = column_key(Sa);
+    const unsigned kb = column_key(Sb);
     // b rides with a if it is in a's cell or the next one up the run axis
     const int dz = pzb - pza;
     const bool ride = act_b && kb == ka && (dz == 0 || dz == 1);
@@ -539,8 +584,12 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
     // second queries that did not ride (other column, or further than one cell away)
     if (!done_b) res_b = eval_direct(Sb, pzb);
 
-    if (act_a) store_q(Sa, qa, res_a);
-    if (act_b) store_q(Sb, qa + 1, res_b);
+    if (act_b && pair_store) {
+      store_pair(Sa, Sb, qa, res_a, res_b);
+    } else {
+      if (act_a) store_q(Sa, qa, res_a);
+      if (act_b) store_q(Sb, qa + 1, res_b);
+    }
   }
 #undef IPXT_WRAP
 #undef IPXT_PERIODIC
