@@ -240,9 +240,8 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
   // period, a guess off by a cell, NaN); (C) weights, fill flags and corner indices.
   // The next round's coordinates wait in shared memory, not in registers (see the loop below),
   // which is what lets the 2 x 3 chains of a 3-D pair fit the 128-register budget.
-  auto locate_range = [&](const T (&qraw)[2][ND], QState<T, ND> (&S)[2], int (&pz)[2], const int k_lo,
-                          const int k_hi) {
-    T q[2][ND], lo[2][ND], hi[2][ND], dxi[2][ND];
+  auto locate_range = [&](const T (&qraw)[2][ND], T (&q)[2][ND], T (&lo)[2][ND], T (&hi)[2][ND], T (&dxi)[2][ND],
+                          QState<T, ND> (&S)[2], int (&pz)[2], const int k_lo, const int k_hi) {
     int ii[2][ND];
     unsigned bad = 0;  // bit 2*ax + k set: entry (k, ax) needs the slow path
     // (A)
@@ -294,26 +293,15 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
         }
       }
     }
-    // (C)
+    // (C) corner indices; the weights follow in form_weights, after the run copy has been issued
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       if (k < k_lo || k >= k_hi) continue;
-      S[k].fill = 0;
 #pragma unroll
       for (int ax = 0; ax < ND; ++ax) {
         const AxisDesc<T>& A = a.ax[ax];
         const int i = ii[k][ax];
         S[k].li[ax] = i;
-        hermite_weights_r<T, ORD0>(q[k][ax], lo[k][ax], hi[k][ax], P.axis[ax].derivative, dxi[k][ax],
-                                   S[k].w[ax]);
-        const ipx_axis_params& pa = P.axis[ax];
-        // a query outside the knots sits in an end cell: the compares run only there
-        if (!IPXT_WRAP(ax) && (i == 1 || i == A.nk - 1)) {
-          const bool flo = !pa.keep_lo && q[k][ax] < AX[ax].x_first;
-          const bool fhi = !pa.keep_hi && q[k][ax] > AX[ax].x_last;
-          S[k].fill |= (flo ? 1u : 0u) << (2 * ax);
-          S[k].fill |= (fhi ? 2u : 0u) << (2 * ax);
-        }
         if (ax < ND - 1) {
           int s0 = i - 2; s0 += s0 < 0 ? A.n : 0;
           int s1 = i - 1; s1 -= s1 >= A.n ? A.n : 0;
@@ -349,6 +337,30 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
       key_ok = key_ok && span < 0xffff0000ull;
     }
   }
+  // (D) weights and fill flags of located queries
+  auto form_weights = [&](const T (&q)[2][ND], const T (&lo)[2][ND], const T (&hi)[2][ND], const T (&dxi)[2][ND],
+                          QState<T, ND> (&S)[2], const int k_hi) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (k >= k_hi) continue;
+      S[k].fill = 0;
+#pragma unroll
+      for (int ax = 0; ax < ND; ++ax) {
+        const int i = S[k].li[ax];
+        hermite_weights_r<T, ORD0>(q[k][ax], lo[k][ax], hi[k][ax], P.axis[ax].derivative, dxi[k][ax],
+                                   S[k].w[ax]);
+        const ipx_axis_params& pa = P.axis[ax];
+        // a query outside the knots sits in an end cell: the compares run only there
+        if (!IPXT_WRAP(ax) && (i == 1 || i == a.ax[ax].nk - 1)) {
+          const bool flo = !pa.keep_lo && q[k][ax] < AX[ax].x_first;
+          const bool fhi = !pa.keep_hi && q[k][ax] > AX[ax].x_last;
+          S[k].fill |= (flo ? 1u : 0u) << (2 * ax);
+          S[k].fill |= (fhi ? 2u : 0u) << (2 * ax);
+        }
+      }
+    }
+  };
+
   auto column_key = [&](const QState<T, ND>& S) {
     unsigned key = 0;
 #pragma unroll
@@ -473,8 +485,13 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
 
     QState<T, ND> SS[2];
     int pzz[2];
-    locate_range(qc, SS, pzz, 0, QPL);
-    if constexpr (!TWO) { SS[1] = SS[0]; pzz[1] = pzz[0]; }
+    T lq[2][ND], llo[2][ND], lhi[2][ND], ldxi[2][ND];
+    locate_range(qc, lq, llo, lhi, ldxi, SS, pzz, 0, QPL);
+    if constexpr (!TWO) {
+      pzz[1] = pzz[0];
+#pragma unroll
+      for (int ax = 0; ax < ND; ++ax) SS[1].li[ax] = SS[0].li[ax];
+    }
     QState<T, ND>& Sa = SS[0];
     QState<T, ND>& Sb = SS[1];
     const int pza = pzz[0], pzb = pzz[1];
@@ -489,53 +506,67 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
     const unsigned mates = __match_any_sync(0xffffffffu, ka);
     const unsigned leaders = __ballot_sync(0xffffffffu, ((__ffs(mates) - 1) == lane) && act_a);
     const bool coherent = key_ok && __popc(leaders) <= kMaxGroups;
+    const int ptop = ride ? pzb : pza;  // highest cell this lane touches in the group pass
+
+    // One group pass = the lanes of one column whose cells fit one run.  begin_pass picks the
+    // next group and ISSUES the copy of its node run (global -> shared, cp.async, no register
+    // staging); the caller waits for it after doing something else.
+    unsigned todo = 0, subm = 0;
+    int zmin = 0;
+    bool sub = false;
+    auto begin_pass = [&]() {
+      const int ld = __ffs(todo) - 1;
+      const unsigned grp = __shfl_sync(0xffffffffu, mates, ld) & todo;
+      const bool in_grp = (grp >> lane) & 1u;
+      zmin = __reduce_min_sync(0xffffffffu, in_grp ? pza : 0x7fffffff);
+      sub = in_grp && (ptop - zmin) <= kRunCap - 2;
+      subm = __ballot_sync(0xffffffffu, sub);
+      const int zmax = __reduce_max_sync(0xffffffffu, sub ? ptop : -0x7fffffff);
+      const int extent = zmax - zmin + 2;  // nodes per column, <= kRunCap
+
+      // node index of (this lane's copy column, run position 0), from the leader's corners
+      int colnode = 0;
+#pragma unroll
+      for (int ax = 0; ax < ND - 1; ++ax) {
+        const int c0 = __shfl_sync(0xffffffffu, Sa.t0[ax], ld);
+        const int c1 = __shfl_sync(0xffffffffu, Sa.t1[ax], ld);
+        colnode = colnode * a.ax[ax].n + (((ccol >> ax) & 1) ? c1 : c0);
+      }
+      // table position of the first node of the run, if the run is contiguous in the table
+      int zt0 = zmin;
+      bool contiguous = run_identity;
+      if (IPXT_PERIODIC(ND - 1)) {
+        zt0 = zmin - 1;
+        contiguous = contiguous && zmin >= 1 && (zmin + extent - 1) <= RA.n;
+      }
+      if (contiguous) {
+        const char* src = tabc + ((size_t)colnode * RA.n + zt0) * Cfg::REC_BYTES + 16 * cl;
+        unsigned dst = cdst0;
+        for (int node = cnode0; node < extent; node += NPR) {
+          cp_async16_s(dst, src);
+          src += NPR * Cfg::REC_BYTES;
+          dst += NPR * Cfg::STRIDE;
+        }
+      } else {
+        for (int node = cnode0; node < extent; node += NPR) {
+          const int zt = run_table_index<T, WM, ND - 1>(RA, zmin + node);
+          cp_async16_s(tile_s + (ccol * kRunCap + node) * Cfg::STRIDE + 16 * cpart,
+                       tabc + ((size_t)colnode * RA.n + zt) * Cfg::REC_BYTES + 16 * cpart);
+        }
+      }
+    };
+    if (coherent) {
+      todo = __ballot_sync(0xffffffffu, act_a);
+      if (todo) begin_pass();
+    }
+    // the weights are formed while the first run copy is in flight
+    form_weights(lq, llo, lhi, ldxi, SS, QPL);
+    if constexpr (!TWO) SS[1] = SS[0];
 
     T res_a = T(0), res_b = T(0);
     bool done_b = !act_b;
     if (coherent) {
-      const int ptop = ride ? pzb : pza;  // highest cell this lane touches in the group pass
-      unsigned todo = __ballot_sync(0xffffffffu, act_a);
       while (todo) {
-        const int ld = __ffs(todo) - 1;
-        const unsigned grp = __shfl_sync(0xffffffffu, mates, ld) & todo;
-        const bool in_grp = (grp >> lane) & 1u;
-        const int zmin = __reduce_min_sync(0xffffffffu, in_grp ? pza : 0x7fffffff);
-        const bool sub = in_grp && (ptop - zmin) <= kRunCap - 2;
-        const unsigned subm = __ballot_sync(0xffffffffu, sub);
-        const int zmax = __reduce_max_sync(0xffffffffu, sub ? ptop : -0x7fffffff);
-        const int extent = zmax - zmin + 2;  // nodes per column, <= kRunCap
-
-        // node index of (this lane's copy column, run position 0), from the leader's corners
-        int colnode = 0;
-#pragma unroll
-        for (int ax = 0; ax < ND - 1; ++ax) {
-          const int c0 = __shfl_sync(0xffffffffu, Sa.t0[ax], ld);
-          const int c1 = __shfl_sync(0xffffffffu, Sa.t1[ax], ld);
-          colnode = colnode * a.ax[ax].n + (((ccol >> ax) & 1) ? c1 : c0);
-        }
-        // table position of the first node of the run, if the run is contiguous in the table
-        int zt0 = zmin;
-        bool contiguous = run_identity;
-        if (IPXT_PERIODIC(ND - 1)) {
-          zt0 = zmin - 1;
-          contiguous = contiguous && zmin >= 1 && (zmin + extent - 1) <= RA.n;
-        }
-        // ---- cooperative copy global -> shared, asynchronous (cp.async, no register staging)
-        if (contiguous) {
-          const char* src = tabc + ((size_t)colnode * RA.n + zt0) * Cfg::REC_BYTES + 16 * cl;
-          unsigned dst = cdst0;
-          for (int node = cnode0; node < extent; node += NPR) {
-            cp_async16_s(dst, src);
-            src += NPR * Cfg::REC_BYTES;
-            dst += NPR * Cfg::STRIDE;
-          }
-        } else {
-          for (int node = cnode0; node < extent; node += NPR) {
-            const int zt = run_table_index<T, WM, ND - 1>(RA, zmin + node);
-            cp_async16_s(tile_s + (ccol * kRunCap + node) * Cfg::STRIDE + 16 * cpart,
-                         tabc + ((size_t)colnode * RA.n + zt) * Cfg::REC_BYTES + 16 * cpart);
-          }
-        }
         cp_async_wait_all();
         __syncwarp();
         if (sub) {
@@ -577,6 +608,7 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
         }
         __syncwarp();
         todo &= ~subm;
+        if (todo) begin_pass();
       }
     } else if (act_a) {
       res_a = eval_direct(Sa, pza);
