@@ -173,14 +173,17 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // permutation (sorted knots, un-padded tables: what Interpolator1D/2D/3D passes); the wrap,
 // seam and fill code of the other axes then drops out of the loop instead of being branched
 // around per query.
-template <typename T, int ND, bool DEVP, bool ORD0, int RC, bool TWO = true, int WM = -1>
+// PM: with WM >= 0, the axes whose padded knot positions map back into an un-padded table (what
+// the Interpolator classes pass: PM == WM); 0 when the periodic tables arrive padded (the
+// functional form, which differentiates the padded table: _spline.py:924-938, 1027-1040).
+template <typename T, int ND, bool DEVP, bool ORD0, int RC, bool TWO = true, int WM = -1, int PM = WM>
 __global__ void __launch_bounds__(tile_max_threads<T>(), 1)
 eval_tile_kernel(const EvalArgs<T, ND> a) {
   constexpr int QPL = TWO ? 2 : 1;  // queries per lane per round
   using Cfg = TileCfg<T, ND, RC, QPL>;
   constexpr bool CTM = WM >= 0;
 #define IPXT_WRAP(AXI) (CTM ? (((WM >> (AXI)) & 1) != 0) : (a.ax[AXI].wrap != 0))
-#define IPXT_PERIODIC(AXI) (CTM ? (((WM >> (AXI)) & 1) != 0) : (a.ax[AXI].periodic != 0))
+#define IPXT_PERIODIC(AXI) (CTM ? (((PM >> (AXI)) & 1) != 0) : (a.ax[AXI].periodic != 0))
 #define IPXT_PERM(AXI) (CTM ? (const int32_t*)nullptr : a.ax[AXI].perm)
   constexpr int kRunCap = RC;
   constexpr int LPC = 32 / Cfg::NC;          // lanes that copy one column
@@ -380,7 +383,7 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
     W.w[0] = S.w;
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk) {
-      const int zt = run_table_index<T, WM, ND - 1>(RA, pz + kk);
+      const int zt = run_table_index<T, PM, ND - 1>(RA, pz + kk);
       T A[1][2];
       layer_contract<T, ND, 1>(
           [&](int c, T* r) {
@@ -549,7 +552,7 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
         }
       } else {
         for (int node = cnode0; node < extent; node += NPR) {
-          const int zt = run_table_index<T, WM, ND - 1>(RA, zmin + node);
+          const int zt = run_table_index<T, PM, ND - 1>(RA, zmin + node);
           cp_async16_s(tile_s + (ccol * kRunCap + node) * Cfg::STRIDE + 16 * cpart,
                        tabc + ((size_t)colnode * RA.n + zt) * Cfg::REC_BYTES + 16 * cpart);
         }
@@ -653,7 +656,7 @@ template <typename T, int ND, int RC, int QPL> static int tile_warps(const EvalA
   return fit >= maxw ? maxw : (fit < 0 ? 0 : (int)fit);
 }
 
-template <typename T, int ND, int RC, bool TWO, int WM>
+template <typename T, int ND, int RC, bool TWO, int WM, int PM = WM>
 static bool launch_tile_wm(const EvalArgs<T, ND>& a, cudaStream_t s) {
   constexpr int QPL = TWO ? 2 : 1;
   const int warps = tile_warps<T, ND, RC, QPL>(a);
@@ -663,8 +666,8 @@ static bool launch_tile_wm(const EvalArgs<T, ND>& a, cudaStream_t s) {
   for (int ax = 0; ax < ND && ord0; ++ax) ord0 = a.hp.axis[ax].derivative <= 0;
   void (*kern)(const EvalArgs<T, ND>);
   if constexpr (WM >= 0) {
-    kern = ord0 ? eval_tile_kernel<T, ND, false, true, RC, TWO, WM>
-                : eval_tile_kernel<T, ND, false, false, RC, TWO, WM>;
+    kern = ord0 ? eval_tile_kernel<T, ND, false, true, RC, TWO, WM, PM>
+                : eval_tile_kernel<T, ND, false, false, RC, TWO, WM, PM>;
   } else {
     kern = a.dp ? eval_tile_kernel<T, ND, true, false, RC, TWO, -1>
                 : (ord0 ? eval_tile_kernel<T, ND, false, true, RC, TWO, -1>
@@ -688,19 +691,27 @@ static bool launch_tile_wm(const EvalArgs<T, ND>& a, cudaStream_t s) {
 // or all but the last axis.  Anything else runs the kernel that reads the flags per query.
 template <typename T, int ND, int RC, bool TWO = true>
 static bool launch_tile_rc(const EvalArgs<T, ND>& a, cudaStream_t s) {
-  int mask = 0;
+  int mask = 0, pmask = 0;
   bool ct = a.dp == nullptr && getenv("IPX_TILE_RUNTIME_FLAGS") == nullptr;
   for (int ax = 0; ax < ND; ++ax) {
     const AxisDesc<T>& A = a.ax[ax];
-    ct = ct && A.perm == nullptr && (A.periodic != 0) == (A.wrap != 0);
+    ct = ct && A.perm == nullptr;
     mask |= (A.wrap != 0) << ax;
+    pmask |= (A.periodic != 0) << ax;
   }
   constexpr int ALL = (1 << ND) - 1;
   constexpr int HEAD = (1 << (ND - 1)) - 1;  // every axis but the last
-  if (ct && mask == 0) return launch_tile_wm<T, ND, RC, TWO, 0>(a, s);
-  if (ct && mask == ALL) return launch_tile_wm<T, ND, RC, TWO, ALL>(a, s);
-  if constexpr (ND > 1) {
-    if (ct && mask == HEAD) return launch_tile_wm<T, ND, RC, TWO, HEAD>(a, s);
+  if (ct && pmask == mask) {  // un-padded tables (Interpolator1D/2D/3D)
+    if (mask == 0) return launch_tile_wm<T, ND, RC, TWO, 0>(a, s);
+    if (mask == ALL) return launch_tile_wm<T, ND, RC, TWO, ALL>(a, s);
+    if constexpr (ND > 1) {
+      if (mask == HEAD) return launch_tile_wm<T, ND, RC, TWO, HEAD>(a, s);
+    }
+  } else if (ct && pmask == 0) {  // padded tables (functional form on periodic axes)
+    if (mask == ALL) return launch_tile_wm<T, ND, RC, TWO, ALL, 0>(a, s);
+    if constexpr (ND > 1) {
+      if (mask == HEAD) return launch_tile_wm<T, ND, RC, TWO, HEAD, 0>(a, s);
+    }
   }
   return launch_tile_wm<T, ND, RC, TWO, -1>(a, s);
 }
