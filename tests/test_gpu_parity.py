@@ -977,3 +977,51 @@ def test_long_knot_vectors_shrink_the_cta(dtype):
                       truth=None if dtype == np.float64 else
                       O.Interpolator3D(upcast(x), upcast(y), upcast(z), upcast(f), "cubic", extrap=True)(
                           upcast(xq[o][:m]), upcast(yq[o][:m]), upcast(zq[o][:m])))
+
+
+# ------------------------------------------------------------------ tile kernel variants
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("ndim", [2, 3])
+@pytest.mark.parametrize("n", [9, 34])
+def test_many_queries_every_periodic_mask(ndim, n, dtype):
+    """Enough queries for the shared-memory tile kernel in BOTH forms (the functional form packs
+    its tables from 2^16 queries up; on periodic axes it hands the kernel PADDED tables, the
+    class un-padded ones), for every set of periodic axes -- none / all / all but the last are
+    compile-time masks in the kernel, the rest read the flags per query -- in cell-sorted and
+    random order (cooperative run copies vs direct gathers), dense and sparse streams (two
+    queries or one per lane), with a derivative on one axis.  Checked against the oracle."""
+    rng = np.random.default_rng(7 * ndim + n)
+    nq = 70_000
+    ns = [n + ax for ax in range(ndim)]
+    knots = [knots_nonuniform(rng, m, 0.0, 1.0 + ax, dtype) for ax, m in enumerate(ns)]
+    f = rng.normal(size=ns).astype(dtype)
+    q = [rng.uniform(-0.6 * (1 + ax), 1.7 * (1 + ax), nq).astype(dtype) for ax in range(ndim)]
+    key = np.zeros(nq, dtype=np.int64)
+    for ax in range(ndim):
+        key = key * (ns[ax] + 2) + np.searchsorted(knots[ax], np.mod(q[ax], (1.0 + ax) * 1.05))
+    order = np.argsort(key, kind="stable")
+    gfun, ofun = (ipx.interp2d, O.interp2d) if ndim == 2 else (ipx.interp3d, O.interp3d)
+    gcls, ocls = (ipx.Interpolator2D, O.Interpolator2D) if ndim == 2 else (ipx.Interpolator3D, O.Interpolator3D)
+    for mask in range(1 << ndim):
+        period = tuple((1.0 + ax) * 1.05 if (mask >> ax) & 1 else None for ax in range(ndim))
+        if mask == 0:
+            period = None
+        extrap = tuple((True, 0.5) for _ in range(ndim))
+        deriv = tuple(1 if ax == mask % ndim else 0 for ax in range(ndim))
+        for qs in ([a[order] for a in q], q):
+            m = 6000  # oracle subsample, spread over the stream
+            sel = np.linspace(0, nq - 1, m).astype(np.int64)
+            got = gfun(*qs, *knots, f, "cubic", deriv, extrap, period)
+            want = ofun(*[a[sel] for a in qs], *knots, f, "cubic", deriv, extrap, period)
+            truth = None
+            if dtype == np.float32:
+                truth = ofun(*[upcast(a[sel]) for a in qs], *[upcast(k) for k in knots], upcast(f), "cubic",
+                             deriv, extrap, period)
+            assert_parity(got[sel], want, f"functional nd={ndim} n={n} mask={mask}", truth)
+            got_c = gcls(*knots, f, "cubic", extrap, period)(*qs, *deriv)
+            want_c = ocls(*knots, f, "cubic", extrap, period)(*[a[sel] for a in qs], *deriv)
+            truth_c = None
+            if dtype == np.float32:
+                truth_c = ocls(*[upcast(k) for k in knots], upcast(f), "cubic", extrap, period)(
+                    *[upcast(a[sel]) for a in qs], *deriv)
+            assert_parity(got_c[sel], want_c, f"class nd={ndim} n={n} mask={mask}", truth_c)
