@@ -267,8 +267,13 @@ def run_ours(args):
         raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly one JSON line.  Libraries write banners to file descriptor 1 on their
+    # own (NCCL prints its version there whatever NCCL_DEBUG_FILE says), so descriptor 1 is pointed
+    # at stderr for the run and the JSON line goes to a private copy of the real stdout.
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own banner / debug lines go to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()  # fail loudly here if libipx.so is missing
@@ -461,7 +466,9 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = {k: v for k, v in cpu_measure(args, 3, 1).items() if k != "ms_per_step"}
-    print(json.dumps(line))
+    if rank == 0:
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     if world > 1:
         dist.destroy_process_group()
 
