@@ -58,6 +58,8 @@ extern "C" {
 #define IPX_SLOPE_MONOTONIC0 4  /* _monotonic, zero end slopes */
 #define IPX_SLOPE_AKIMA 5       /* _akima       _fd_derivs.py:390-424 */
 #define IPX_SLOPE_ZERO 6        /* nearest / linear -> zeros, _fd_derivs.py:72-73 */
+#define IPX_SLOPE_AKIMA_COMPLEX 7 /* _akima on complex data: `inner` counts real elements, (re, im) pairs;
+                                     the weights are moduli of complex differences (jnp.abs, :414) */
 
 /* cubic2 boundary conditions (_fd_derivs.py:104-157) */
 #define IPX_BC_NOT_A_KNOT 0

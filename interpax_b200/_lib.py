@@ -17,6 +17,7 @@ IPX_NEAREST, IPX_LINEAR, IPX_CUBIC = 0, 1, 2
 IPX_SOA, IPX_AOS = 0, 1
 IPX_SLOPE_CUBIC, IPX_SLOPE_CUBIC2, IPX_SLOPE_CARDINAL = 0, 1, 2
 IPX_SLOPE_MONOTONIC, IPX_SLOPE_MONOTONIC0, IPX_SLOPE_AKIMA, IPX_SLOPE_ZERO = 3, 4, 5, 6
+IPX_SLOPE_AKIMA_COMPLEX = 7
 IPX_PPOLY_NAN, IPX_PPOLY_EXTRAPOLATE, IPX_PPOLY_PERIODIC = 0, 1, 2
 IPX_BC_NOT_A_KNOT, IPX_BC_FIRST, IPX_BC_SECOND = 0, 1, 2
 

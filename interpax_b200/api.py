@@ -175,8 +175,11 @@ def _suffix(t: torch.Tensor) -> str:
 
 
 # --------------------------------------------------------------------------- device-side ops
-def _slopes_dev(x: torch.Tensor, f: torch.Tensor, method: str, axis: int, kwargs: dict) -> torch.Tensor:
-    """approx_df on device tensors (real dtype, C-contiguous)."""
+def _slopes_dev(x: torch.Tensor, f: torch.Tensor, method: str, axis: int, kwargs: dict,
+                cplx: bool = False) -> torch.Tensor:
+    """approx_df on device tensors (real dtype, C-contiguous).  ``cplx``: ``f`` is complex data
+    viewed as a trailing (re, im) pair; only akima needs to know (its weights are moduli of
+    complex differences, _fd_derivs.py:414), every other method acts on the parts separately."""
     errorif(method not in _SLOPE_CODE, ValueError, f"got unknown method {method}")
     lib = L.load()
     axis = axis % f.ndim
@@ -185,6 +188,9 @@ def _slopes_dev(x: torch.Tensor, f: torch.Tensor, method: str, axis: int, kwargs
     outer = int(np.prod(f.shape[:axis], dtype=np.int64))
     inner = int(np.prod(f.shape[axis + 1:], dtype=np.int64))
     code = _SLOPE_CODE[method]
+    if cplx and method == "akima":
+        errorif(axis == f.ndim - 1, ValueError, "the (re, im) pair axis cannot be differentiated")
+        code = L.IPX_SLOPE_AKIMA_COMPLEX
     opts = L.SlopeOpts()
     opts.c = float(kwargs.get("c", 0)) if method == "cardinal" else 0.0
     keep = []
@@ -566,8 +572,6 @@ def _interp(ndim, qs, knots, f, method, derivative, extrap, period, kwargs, retu
     errorif(method not in methods, ValueError, f"unknown method {method}")
     io = _Inputs(qs, knots, f)
     kn = [io.coords(k) for k in knots]
-    errorif(io.complex and method == "akima" and any(v is None for v in given.values()),
-            NotImplementedError, "akima slopes of complex data are not implemented")
 
     periods = _parse_ndarg(period, ndim)
     derivs = _parse_ndarg(derivative, ndim)
@@ -612,7 +616,7 @@ def _interp(ndim, qs, knots, f, method, derivative, extrap, period, kwargs, retu
         if packed is None:
             for name, src, ax in CHAIN[ndim]:
                 if tabs[name] is None:
-                    tabs[name] = _slopes_dev(kuse[ax], tabs[src], method, ax, kwargs)
+                    tabs[name] = _slopes_dev(kuse[ax], tabs[src], method, ax, kwargs, io.complex)
             for n in names[1:]:
                 errorif(tabs[n].shape != tabs["f"].shape, ValueError,
                         f"{n} must have the same shape as f")
@@ -677,8 +681,6 @@ def approx_df(x, f, method="cubic", axis=-1, **kwargs):
     fdt = _promote([f])
     xdt = _promote([x])
     cplx = bool(np.issubdtype(fdt, np.complexfloating))
-    errorif(cplx and method == "akima", NotImplementedError,
-            "akima slopes of complex data are not implemented")
     rdt = np.dtype(np.float64) if fdt in (np.float64, np.complex128) else np.dtype(np.float32)
     ft = _to_dev(f, fdt, dev)
     nd = ft.ndim
@@ -686,7 +688,7 @@ def approx_df(x, f, method="cubic", axis=-1, **kwargs):
     if cplx:
         ft = torch.view_as_real(ft).contiguous()
     xt = _to_dev(x, xdt, dev).to(_NP2T[rdt])
-    out = _slopes_dev(xt, ft, method, axis, kwargs)
+    out = _slopes_dev(xt, ft, method, axis, kwargs, cplx)
     if cplx:
         out = torch.view_as_complex(out)
     return out if want_torch else out.cpu().numpy()
@@ -824,8 +826,6 @@ class _InterpolatorND:
         io = _Inputs((), knots, f)
         kn = [io.coords(k) for k in knots]
         errorif(ndim == 1 and self.axis != 0, NotImplementedError, "only axis=0 is supported")
-        errorif(io.complex and method == "akima" and any(v is None for v in given.values()),
-                NotImplementedError, "akima slopes of complex data are not implemented")
         self.method = method
         self.extrap = extrap
         self.period = period
@@ -847,7 +847,7 @@ class _InterpolatorND:
             tabs[n] = None if given[n] is None else io.table(given[n])
         for name, src, ax in CHAIN[ndim]:
             if tabs[name] is None:
-                tabs[name] = _slopes_dev(kn[ax], tabs[src], method, ax, kwargs)
+                tabs[name] = _slopes_dev(kn[ax], tabs[src], method, ax, kwargs, io.complex)
         self._tabs = tabs
         if _method_class(method) == L.IPX_CUBIC:
             self._packed = _pack_dev(ndim, [tabs[n] for n in names])

@@ -219,6 +219,82 @@ __global__ void slopes_akima_kernel(const SlopeArgs<T> a, const T* __restrict__ 
   }
 }
 
+// Complex data (IPX_SLOPE_AKIMA_COMPLEX): `inner` counts REAL elements and is even, every
+// (re, im) pair is one complex value.  The extended secants are linear, so each part goes through
+// akima_m on its own; only the weights |m4 - m3|, |m2 - m1| (jnp.abs of a complex difference,
+// _fd_derivs.py:414) and the global maximum of their sum couple the two parts.
+template <typename T> __device__ __forceinline__ T t_hypot(T a, T b);
+template <> __device__ __forceinline__ float t_hypot<float>(float a, float b) { return hypotf(a, b); }
+template <> __device__ __forceinline__ double t_hypot<double>(double a, double b) { return hypot(a, b); }
+
+template <typename T>
+__device__ __forceinline__ void split_index_pairs(const SlopeArgs<T>& a, int64_t e, int64_t& base, int& k) {
+  const int64_t half = a.inner >> 1;
+  int64_t i = e % half;
+  int64_t r = e / half;
+  k = (int)(r % a.n);
+  int64_t o = r / a.n;
+  base = o * a.n * a.inner + 2 * i;  // real part of element k = 0 of this column
+}
+
+template <typename T> struct AkimaPair {
+  T w43, w21, m1[2], m2[2], m3[2], m4[2];
+};
+template <typename T>
+__device__ __forceinline__ void akima_pair(const SlopeArgs<T>& a, int64_t base, int k, AkimaPair<T>& p) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    p.m1[c] = akima_m(a, base + c, k);
+    p.m2[c] = akima_m(a, base + c, k + 1);
+    p.m3[c] = akima_m(a, base + c, k + 2);
+    p.m4[c] = akima_m(a, base + c, k + 3);
+  }
+  p.w43 = t_hypot(p.m4[0] - p.m3[0], p.m4[1] - p.m3[1]);
+  p.w21 = t_hypot(p.m2[0] - p.m1[0], p.m2[1] - p.m1[1]);
+}
+
+template <typename T>
+__global__ void akima_max_complex_kernel(const SlopeArgs<T> a, T* __restrict__ gmax) {
+  const int64_t total = a.outer * a.n * (a.inner >> 1);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  T local = T(0);
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    int64_t base; int k;
+    split_index_pairs(a, e, base, k);
+    AkimaPair<T> p;
+    akima_pair(a, base, k, p);
+    T f12 = p.w43 + p.w21;
+    if (f12 > local) local = f12;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    T o = __shfl_xor_sync(0xffffffffu, local, off);
+    if (o > local) local = o;
+  }
+  if ((threadIdx.x & 31) == 0 && local > T(0)) atomic_max_nonneg(gmax, local);
+}
+
+template <typename T>
+__global__ void slopes_akima_complex_kernel(const SlopeArgs<T> a, const T* __restrict__ gmax) {
+  const int64_t total = a.outer * a.n * (a.inner >> 1);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const T thresh = T(1e-9) * (*gmax);
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    int64_t base; int k;
+    split_index_pairs(a, e, base, k);
+    AkimaPair<T> p;
+    akima_pair(a, base, k, p);
+    const T f12 = p.w43 + p.w21;
+    const bool mask = f12 > thresh;
+    const T den = mask ? f12 : T(1);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      T df = (p.w43 * p.m2[c] + p.w21 * p.m3[c]) / den;
+      a.out[base + (int64_t)k * a.inner + c] = mask ? df : T(0.5) * (p.m4[c] + p.m1[c]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ cubic2 (_cubic2)
 template <typename T> struct BcArgs {
   int32_t start, end;                       // IPX_BC_*
@@ -533,6 +609,15 @@ static int launch_slopes(const T* x, int32_t n, const T* f, int64_t outer, int64
       akima_init_kernel<T><<<1, 1, 0, s>>>(gmax);
       akima_max_kernel<T><<<grid, kSlopeThreads, 0, s>>>(a, gmax);
       slopes_akima_kernel<T><<<grid, kSlopeThreads, 0, s>>>(a, gmax);
+      break;
+    }
+    case IPX_SLOPE_AKIMA_COMPLEX: {
+      if (n < 2 || workspace == nullptr || (inner & 1) != 0) return IPX_EINVAL;
+      T* gmax = static_cast<T*>(workspace);
+      const int cgrid = slope_grid(total / 2);
+      akima_init_kernel<T><<<1, 1, 0, s>>>(gmax);
+      akima_max_complex_kernel<T><<<cgrid, kSlopeThreads, 0, s>>>(a, gmax);
+      slopes_akima_complex_kernel<T><<<cgrid, kSlopeThreads, 0, s>>>(a, gmax);
       break;
     }
     case IPX_SLOPE_CUBIC2: {
@@ -915,7 +1000,7 @@ static int launch_slopes_pack(int32_t ndim, const T* const* knots, const int32_t
   if (ndim == 1) return IPX_EUNSUPPORTED;  // two tables: slopes + pack is already one pass each
   if (method != IPX_SLOPE_CUBIC && method != IPX_SLOPE_CARDINAL && method != IPX_SLOPE_MONOTONIC &&
       method != IPX_SLOPE_MONOTONIC0)
-    return (method >= 0 && method <= IPX_SLOPE_ZERO) ? IPX_EUNSUPPORTED : IPX_EINVAL;
+    return (method >= 0 && method <= IPX_SLOPE_AKIMA_COMPLEX) ? IPX_EUNSUPPORTED : IPX_EINVAL;
   FusedArgs<T> a{};
   int64_t total = batch, knots_total = 0;
   for (int ax = 0; ax < ndim; ++ax) {
@@ -959,7 +1044,7 @@ extern "C" int ipx_slopes_pack_f64(int32_t ndim, const double* const* knots, con
 }
 
 extern "C" size_t ipx_slopes_workspace_bytes(int32_t method, int32_t n, int32_t elem_size) {
-  if (method == IPX_SLOPE_AKIMA) return 16;
+  if (method == IPX_SLOPE_AKIMA || method == IPX_SLOPE_AKIMA_COMPLEX) return 16;
   if (method == IPX_SLOPE_CUBIC2) return (size_t)2 * (size_t)(n > 0 ? n : 0) * (size_t)elem_size + 16;
   return 0;
 }

@@ -330,11 +330,9 @@ class CubicHermiteSpline(PPoly):
 
 def _knot_slopes(xt, yt, method, axis, kwargs):
     """approx_df on device tensors; complex data as a trailing real pair."""
-    errorif(yt.is_complex() and method == "akima", NotImplementedError,
-            "akima slopes of complex data are not implemented")
     if yt.is_complex():
         out = _slopes_dev(xt.to(_NP2T[_real_of(_T2NP[yt.dtype])]), torch.view_as_real(yt).contiguous(), method,
-                          axis, kwargs)
+                          axis % yt.ndim, kwargs, True)
         return torch.view_as_complex(out)
     return _slopes_dev(xt.to(yt.dtype), yt.contiguous(), method, axis, kwargs)
 

@@ -133,6 +133,37 @@ def test_slopes_vs_oracle(method, dtype):
         assert_parity(got, want.astype(dtype), f"{method} {shape} axis={axis}")
 
 
+@pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
+def test_slopes_complex_data(dtype):
+    """Complex `f` (the reference's tests run every method on complex data,
+    tests/test_interpolate.py:28-81): all methods but akima act on the two parts separately;
+    akima weighs with moduli of complex differences (_fd_derivs.py:414)."""
+    rng = np.random.default_rng(5)
+    rdt = np.float32 if dtype == np.complex64 else np.float64
+    for shape, axis in [((40,), 0), ((33, 5), 0), ((4, 29), 1), ((3, 17, 6), 1), ((5, 4, 21), -1),
+                        ((2,), 0), ((3,), 0), ((4,), 0), ((3, 2), 0)]:
+        n = shape[axis]
+        x = knots_nonuniform(rng, n, 0, 2, rdt)
+        f = (rng.normal(size=shape) + 1j * rng.normal(size=shape)).astype(dtype)
+        if n >= 12:
+            sl = [slice(None)] * len(shape)
+            sl[axis] = slice(5, 9)
+            f[tuple(sl)] = 0.25 - 1.5j  # flat stretch: degenerate akima weights -> 0.5 (m1 + m4)
+        for method in O.CUBIC_METHODS:
+            want = O.approx_df(x, f, method, axis)
+            got = ipx.approx_df(x, f, method, axis)
+            assert got.dtype == dtype
+            assert_parity(got, want.astype(dtype), f"{method} {shape} axis={axis}")
+    # 2-D: the slope chain fx, fy, fxy on complex data, functional and class form
+    xk, yk = knots_nonuniform(rng, 11, 0, 1, rdt), knots_nonuniform(rng, 9, 0, 2, rdt)
+    f = (rng.normal(size=(11, 9)) + 1j * rng.normal(size=(11, 9))).astype(dtype)
+    xq, yq = rng.uniform(0, 1, 300).astype(rdt), rng.uniform(0, 2, 300).astype(rdt)
+    want = O.interp2d(xq, yq, xk, yk, f, "akima")
+    assert_parity(ipx.interp2d(xq, yq, xk, yk, f, "akima"), want, "interp2d akima complex")
+    assert_parity(ipx.Interpolator2D(xk, yk, f, "akima")(xq, yq), O.Interpolator2D(xk, yk, f, "akima")(xq, yq),
+                  "Interpolator2D akima complex")
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_slopes_duplicate_knots_and_flat_data(dtype):
     rng = np.random.default_rng(4)
@@ -383,10 +414,6 @@ def test_reference_test_interp1d(dtype, scalar):
     x = 0.0 if scalar else np.real(np.linspace(0, 2 * np.pi, 10000).astype(dtype))
     for interp in (ipx.interp1d, lambda xq, *a, **k: ipx.Interpolator1D(*a, **k)(xq)):
         for m, (rtol, atol) in TOL_1D.items():
-            if cplx and m == "akima":
-                with pytest.raises(NotImplementedError):
-                    interp(x, xp, fp, method=m)
-                continue
             fq = interp(x, xp, fp, method=m)
             assert fq.dtype == np.result_type(x, xp, fp), m
             np.testing.assert_allclose(fq, f(x), rtol=rtol, atol=atol, err_msg=m)
@@ -437,8 +464,6 @@ def test_reference_test_interp2d(dtype, scalar):
     for form, interp in (("fn", ipx.interp2d), ("cls", lambda xq, yq, *a, **k: ipx.Interpolator2D(*a, **k)(xq, yq))):
         ointerp = O.interp2d if form == "fn" else (lambda xq, yq, *a, **k: O.Interpolator2D(*a, **k)(xq, yq))
         for m, (rtol, atol) in tol.items():
-            if cplx and m == "akima":
-                continue
             fq = interp(x, y, xp, yp, fp, method=m, period=per)
             assert fq.dtype == np.result_type(x, y, xp, yp, fp)
             np.testing.assert_allclose(fq, f(x, y), rtol=rtol, atol=atol, err_msg=m)
