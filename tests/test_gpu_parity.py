@@ -1050,3 +1050,26 @@ def test_many_queries_every_periodic_mask(ndim, n, dtype):
                 truth_c = ocls(*[upcast(k) for k in knots], upcast(f), "cubic", extrap, period)(
                     *[upcast(a[sel]) for a in qs], *deriv)
             assert_parity(got_c[sel], want_c, f"class nd={ndim} n={n} mask={mask}", truth_c)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_unaligned_out_and_odd_counts(dtype):
+    """The tile kernel stores a lane's two results as one 16-byte (f64) / 8-byte (f32) word when
+    `out` allows it: an `out` that starts one element into a buffer, and odd query counts, must
+    give the same bits through the element-wise store."""
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(77)
+    n = 20
+    k = torch.linspace(0, 1, n, dtype=dtype, device=dev)
+    f = torch.randn((n, n, n), dtype=dtype, device=dev, generator=g)
+    ip = ipx.Interpolator3D(k, k, k, f, "cubic", ((True, True), (0.5, True), (False, False)), (None, None, 1.25))
+    for nq in (1, 2, 63, 64, 65, 4097, 100_001):
+        q = [(torch.rand(nq, dtype=dtype, device=dev, generator=g) * 1.4 - 0.2) for _ in range(3)]
+        want = ip(*q)
+        buf = torch.full((nq + 3,), -5.0, dtype=dtype, device=dev)
+        for off in (0, 1, 2):
+            buf.fill_(-5.0)
+            ret = ip(*q, out=buf[off:off + nq])
+            assert torch.equal(torch.nan_to_num(ret, nan=-7.0), torch.nan_to_num(want, nan=-7.0)), (nq, off)
+            # nothing written outside the window
+            assert torch.all(buf[:off] == -5.0) and torch.all(buf[off + nq:] == -5.0), (nq, off)
