@@ -39,9 +39,28 @@ namespace ipx {
 // float64 kernel (128 registers) or 20 of a float32 one (96; measured against 16 and 24 warps,
 // profiles/ in the DESIGN table); the launch uses fewer warps when long knot vectors leave less
 // room for the per-warp tiles.
+#ifndef IPX_TILE_PAD
+#define IPX_TILE_PAD 1
+#endif
 #ifndef IPX_TILE_F64_THREADS
 #define IPX_TILE_F64_THREADS 512
 #endif
+// smallest node spacing for which the 8 / ch lane groups of a quarter warp (ch 16-byte chunks
+// each, node stride = stride_chunks chunks) write 8 different bank groups
+__host__ __device__ constexpr int copy_node_spacing(int stride_chunks, int ch) {
+  for (int sp = 1; sp <= 8; ++sp) {
+    unsigned used = 0;
+    bool ok = true;
+    for (int g = 0; g < 8 / ch; ++g)
+      for (int c = 0; c < ch; ++c) {
+        const unsigned bit = 1u << ((g * sp * stride_chunks + c) % 8);
+        ok = ok && (used & bit) == 0;
+        used |= bit;
+      }
+    if (ok) return sp;
+  }
+  return 1;
+}
 template <typename T> constexpr int tile_max_threads() { return sizeof(T) == 4 ? 640 : IPX_TILE_F64_THREADS; }
 constexpr int kMaxGroups = 4;       // more distinct columns than this in a warp -> direct path
 constexpr int kSmemKnotCap = 6144;  // total knots (all axes) staged in shared memory
@@ -53,7 +72,7 @@ template <typename T, int ND, int RC = 16, int QPL = 2> struct TileCfg {
   static constexpr int NCA = ND > 1 ? ND - 1 : 1;          // column axes (array extent)
   static constexpr int REC_BYTES = NT * (int)sizeof(T);
   static constexpr int CH = REC_BYTES / 16;                // 16-byte chunks per record
-  static constexpr int STRIDE = REC_BYTES + (REC_BYTES >= 32 ? 16 : 0);  // bank-conflict padding
+  static constexpr int STRIDE = REC_BYTES + (IPX_TILE_PAD && REC_BYTES >= 32 ? 16 : 0);  // bank-conflict padding
   static constexpr int RUN_BYTES = NC * RC * STRIDE;         // node runs of one group
   static constexpr int QSLOT = QPL * (int)sizeof(T);         // a lane's coordinates on one axis
   static constexpr int QAXIS = 32 * QSLOT;
@@ -189,6 +208,13 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
   constexpr int LPC = 32 / Cfg::NC;          // lanes that copy one column
   constexpr int NPR = LPC / Cfg::CH;         // nodes of a column copied per round
   static_assert(LPC % Cfg::CH == 0 && NPR >= 1, "column copy layout");
+  // One cp.async instruction writes, per column, the 16-byte chunks of NPR nodes; a quarter
+  // warp's 8 chunks land in one shared-memory wavefront only if they hit 8 different 16-byte bank
+  // groups.  With the padded node stride, nodes that are neighbours collide (80 B: node n+1
+  // wraps onto node n's first group), nodes SP apart do not, SP = the spacing for which
+  // SP * STRIDE advances the bank group by exactly one record: lane group g copies nodes
+  // base + j + SP * g, j = 0 .. SP-1.
+  constexpr int SP = copy_node_spacing(Cfg::STRIDE / 16, Cfg::CH);
   extern __shared__ __align__(16) char smem[];
   __shared__ TileAxis<T> AX[ND];
   __shared__ ipx_params params_s;  // only used when the traced operands live in device memory
@@ -233,7 +259,7 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
   const int cnode0 = cl / Cfg::CH;
   const int cpart = cl - cnode0 * Cfg::CH;
   const unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);
-  const unsigned cdst0 = tile_s + (ccol * kRunCap + cnode0) * Cfg::STRIDE + 16 * cpart;
+  const unsigned cdst0 = tile_s + (ccol * kRunCap + SP * cnode0) * Cfg::STRIDE + 16 * cpart;
 
   // ---- locate both queries of the lane ---------------------------------------------------
   // Written as three straight-line phases so that the 2 x ND independent dependency chains
@@ -543,12 +569,15 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
         contiguous = contiguous && zmin >= 1 && (zmin + extent - 1) <= RA.n;
       }
       if (contiguous) {
-        const char* src = tabc + ((size_t)colnode * RA.n + zt0) * Cfg::REC_BYTES + 16 * cl;
+        const char* src =
+            tabc + ((size_t)colnode * RA.n + zt0) * Cfg::REC_BYTES + (SP * cnode0) * Cfg::REC_BYTES + 16 * cpart;
         unsigned dst = cdst0;
-        for (int node = cnode0; node < extent; node += NPR) {
-          cp_async16_s(dst, src);
-          src += NPR * Cfg::REC_BYTES;
-          dst += NPR * Cfg::STRIDE;
+        for (int node = SP * cnode0; node < extent + SP * cnode0; node += SP * NPR) {
+#pragma unroll
+          for (int j = 0; j < SP; ++j)
+            if (node + j < extent) cp_async16_s(dst + j * Cfg::STRIDE, src + j * Cfg::REC_BYTES);
+          src += SP * NPR * Cfg::REC_BYTES;
+          dst += SP * NPR * Cfg::STRIDE;
         }
       } else {
         for (int node = cnode0; node < extent; node += NPR) {
