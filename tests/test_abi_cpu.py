@@ -126,3 +126,17 @@ def test_no_cpu_fallback():
     for fn in os.listdir(pkg):
         if fn.endswith(".py"):
             assert "oracle" not in open(os.path.join(pkg, fn)).read().replace("no oracle", ""), fn
+
+
+def test_header_constants_match_the_python_mirror():
+    """Every integer `#define IPX_*` of include/ipx.h that interpax_b200/_lib.py mirrors has the
+    same value there (method classes, layouts, slope codes, boundary kinds, error codes)."""
+    src = open(HEADER).read()
+    defines = {m.group(1): int(m.group(2), 0)
+               for m in re.finditer(r"^#define\s+(IPX_[A-Z0-9_]+)\s+\(?(-?(?:0x)?[0-9a-fA-F]+)\)?\s*(?:/\*.*)?$",
+                                    src, re.M)}
+    assert "IPX_SLOPE_AKIMA_COMPLEX" in defines and "IPX_OK" in defines
+    mirrored = [n for n in defines if hasattr(_lib, n) and isinstance(getattr(_lib, n), int)]
+    assert len(mirrored) >= 15, mirrored
+    for n in mirrored:
+        assert getattr(_lib, n) == defines[n], n
