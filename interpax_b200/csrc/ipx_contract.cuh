@@ -31,6 +31,28 @@ template <typename T, int NT> __device__ __forceinline__ void ldg_record(const T
   if (NT == 8) ldg_rec8(p, r);
 }
 
+// 256-bit read-only global loads (sm_100: LDG.E.256): half the load instructions and L1 requests
+// of the direct gathers.  The record must be 32-byte aligned.
+__device__ __forceinline__ void ldg256(const double* p, double* r) {
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r[0]), "=d"(r[1]), "=d"(r[2]), "=d"(r[3]) : "l"(p));
+}
+__device__ __forceinline__ void ldg256(const float* p, float* r) {
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+      : "l"(p));
+}
+template <typename T, int NT> __device__ __forceinline__ void ldg_record_wide(const T* p, T* r) {
+  constexpr int BYTES = NT * (int)sizeof(T);
+  if constexpr (BYTES == 64) {
+    ldg256(p, r);
+    ldg256(p + NT / 2, r + NT / 2);
+  } else if constexpr (BYTES == 32) {
+    ldg256(p, r);
+  } else {
+    ldg_record<T, NT>(p, r);
+  }
+}
+
 // weights of NQ queries that walk a layer together
 template <typename T, int ND, int NQ> struct WeightRefs {
   const T (*w[NQ])[4];

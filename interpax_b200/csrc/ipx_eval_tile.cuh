@@ -417,7 +417,7 @@ eval_tile_kernel(const EvalArgs<T, ND> a) {
 #pragma unroll
             for (int ax = 0; ax < ND - 1; ++ax) node = node * a.ax[ax].n + (((c >> ax) & 1) ? S.t1[ax] : S.t0[ax]);
             node = node * RA.n + zt;
-            ldg_record<T, Cfg::NT>(reinterpret_cast<const T*>(tabc) + node * Cfg::NT, r);
+            ldg_record_wide<T, Cfg::NT>(reinterpret_cast<const T*>(tabc) + node * Cfg::NT, r);
           },
           W, A);
       res = finish_layer(S, A[0], kk, res);
@@ -763,7 +763,7 @@ static bool launch_tile(const EvalArgs<T, ND>& a, cudaStream_t s) {
       if ((reinterpret_cast<uintptr_t>(a.ax[ax].q) & 15) != 0) return false;
     }
     if (total_knots > kSmemKnotCap) return false;
-    if ((reinterpret_cast<uintptr_t>(a.tab[0]) & 15) != 0) return false;
+    if ((reinterpret_cast<uintptr_t>(a.tab[0]) & 31) != 0) return false;  // 256-bit direct gathers
     // Queries per cell decide the shape of a warp's round (measured on 256^3 / 512^3 f64,
     // profiles/sweep_tile_modes.sh): from about three per cell up, two consecutive queries
     // per lane share node layers; below that a lane's pair is rarely in adjacent cells and a
