@@ -146,6 +146,69 @@ IPX_DECL_EVAL(f32, float)
 IPX_DECL_EVAL(f64, double)
 
 /* ---------------------------------------------------------------------------------
+ * Cubic evaluation straight from f for the three-point slope stencils.
+ * For method = cubic (_fd_derivs.py:79-101), cardinal and catmull-rom (:303-324) every link of
+ * the slope chain fx, fy, fz, fxy, ... (interpax/_spline.py:380-393 classes, :1027-1040
+ * functional form) is linear in f and acts along one axis, so
+ *   interpNd(q, knots, f, method)      ==  sum over the 4^d neighbourhood of f, weights Tx (x) Ty (x) Tz
+ * with four tap weights per axis (Hermite weights composed with the stencil).  These two entry
+ * points replace the slope chain + gather + A_CUBIC/A_BICUBIC/A_TRICUBIC contraction
+ * (_spline.py:572-589, 759-800, 1027-1099) and, through the mask bits, both periodic
+ * conventions of the reference without materialising a padded table per call.
+ *
+ * ipx_halo_table_*: out = f (C order, extents n[ax], scalar-valued) copied into the halo layout,
+ *   extent n[ax] + 2 on an open axis, n[ax] + 4 on a periodic one (mask bits as for
+ *   ipx_eval_stencil_*; perm from ipx_periodic_knots_*, NULL = identity; perm itself a HOST array
+ *   of ndim device pointers or NULL).  Entry u holds the value at lookup-knot position u - 1:
+ *   open axis: f[u-1], and one GHOST row beyond each end, 2 f[0] - f[1] resp. 2 f[n-1] - f[n-2],
+ *   with which the centred stencil at the end knot equals the reference's one-sided one;
+ *   IPX_PERIODIC: f[perm[(u-2) mod n]] throughout; IPX_PAD_FIRST: the same for the padded
+ *   positions 0 .. n+1 and ghost rows beyond them.
+ * ipx_eval_stencil_*: q / knots / slope_knots are HOST arrays of ndim device pointers.
+ *   periodic_mask bit a (IPX_PERIODIC): Interpolator* convention -- knots[a] are the n+2 padded
+ *   sorted knots, slope_knots[a] the n original knots the slopes are taken on (one-sided at table
+ *   rows 0 and n-1, then wrapped; the knots must already be sorted inside one period);
+ *   bit 4+a (IPX_PAD_FIRST): functional-form convention -- slopes are taken on the padded knots
+ *   (_spline.py:924-938 precede :1027-1040).  Open axes: knots[a] = the n knots.  slope_knots may
+ *   be NULL when no axis uses IPX_PERIODIC.
+ *   slope_method IPX_SLOPE_CUBIC or IPX_SLOPE_CARDINAL (c = tension; catmull-rom: c = 0).
+ *   records: NULL, or the IPX_AOS records of the same tables (ipx_slopes_pack_* / ipx_pack_*; of the
+ *   PADDED tables on IPX_PAD_FIRST axes).  With IPX_STENCIL_AUTO they serve the streams on which the
+ *   record form measures faster (dense cell-sorted 3-D streams; random order on tables much larger
+ *   than L2, and in 2-D).
+ *   hint: IPX_STENCIL_SPARSE = one query per lane; IPX_STENCIL_DENSE = four consecutive queries per
+ *   lane share the table rows, staged in shared memory (for cell-sorted streams with several
+ *   queries per cell; any stream is still evaluated correctly); IPX_STENCIL_AUTO chooses, and if
+ *   `workspace` (NULL, or 4 int32 of device scratch) is given it chooses ON THE DEVICE: a probe
+ *   kernel classifies a sample of the stream (dense cell-sorted / cell-sorted / random), every
+ *   candidate kernel is enqueued and the ones not chosen return at once -- no host
+ *   synchronisation, so the call stays CUDA-graph capturable.
+ *   Returns IPX_EUNSUPPORTED when the knot vectors do not fit in shared memory
+ *   (the caller then uses ipx_slopes_pack_* + ipx_eval*).
+ *   params / out / idx_out / stream as for ipx_eval*.
+ * --------------------------------------------------------------------------------- */
+#define IPX_PAD_FIRST(axis) (1 << (4 + (axis)))
+#define IPX_STENCIL_AUTO 0
+#define IPX_STENCIL_SPARSE 1
+#define IPX_STENCIL_DENSE 2
+/* elements of the halo table (the last axis is padded to a multiple of 32 bytes), or -1 */
+int64_t ipx_halo_table_elems(int32_t ndim, const int32_t* n, int32_t periodic_mask, int32_t elem_size);
+int ipx_halo_table_f32(int32_t ndim, const float* f, const int32_t* n, int32_t periodic_mask,
+                       const int32_t* const* perm, float* out, void* stream);
+int ipx_halo_table_f64(int32_t ndim, const double* f, const int32_t* n, int32_t periodic_mask,
+                       const int32_t* const* perm, double* out, void* stream);
+int ipx_eval_stencil_f32(int32_t ndim, const float* const* q, int64_t nq, const float* const* knots,
+                         const float* const* slope_knots, const int32_t* n, const float* halo, const float* records,
+                         int32_t slope_method, double c, int32_t periodic_mask, const ipx_params* params,
+                         int32_t params_on_device, float* out, int32_t* idx_out, int32_t hint,
+                         int32_t* workspace, void* stream);
+int ipx_eval_stencil_f64(int32_t ndim, const double* const* q, int64_t nq, const double* const* knots,
+                         const double* const* slope_knots, const int32_t* n, const double* halo, const double* records,
+                         int32_t slope_method, double c, int32_t periodic_mask, const ipx_params* params,
+                         int32_t params_on_device, double* out, int32_t* idx_out, int32_t hint,
+                         int32_t* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------
  * Interval lookup alone: idx[k] = clip(searchsorted(knots, q[k], side="right"), 1, n-1).
  * Replaces the jnp.searchsorted + jnp.clip pair at interpax/_spline.py:543,556,571,
  * 708-709,729-730,767-768,946-948,983-985,1051-1053.

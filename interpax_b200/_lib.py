@@ -20,6 +20,7 @@ IPX_SLOPE_MONOTONIC, IPX_SLOPE_MONOTONIC0, IPX_SLOPE_AKIMA, IPX_SLOPE_ZERO = 3, 
 IPX_SLOPE_AKIMA_COMPLEX = 7
 IPX_PPOLY_NAN, IPX_PPOLY_EXTRAPOLATE, IPX_PPOLY_PERIODIC = 0, 1, 2
 IPX_BC_NOT_A_KNOT, IPX_BC_FIRST, IPX_BC_SECOND = 0, 1, 2
+IPX_STENCIL_AUTO, IPX_STENCIL_SPARSE, IPX_STENCIL_DENSE = 0, 1, 2
 
 
 def IPX_PERIODIC(axis: int) -> int:
@@ -27,6 +28,10 @@ def IPX_PERIODIC(axis: int) -> int:
 
 
 def IPX_WRAP_ONLY(axis: int) -> int:
+    return 1 << (4 + axis)
+
+
+def IPX_PAD_FIRST(axis: int) -> int:
     return 1 << (4 + axis)
 
 
@@ -59,11 +64,11 @@ class SlopeOpts(C.Structure):
 # every symbol include/ipx.h declares; tests/test_abi.py checks the .so exports them all
 SYMBOLS = (
     ["ipx_version", "ipx_build_info", "ipx_slopes_workspace_bytes", "ipx_cell_order_workspace_bytes",
-     "ipx_cell_sort_workspace_bytes"]
+     "ipx_cell_sort_workspace_bytes", "ipx_halo_table_elems"]
     + [f"ipx_eval{d}d_{t}" for d in (1, 2, 3) for t in ("f32", "f64")]
     + [
         f"ipx_{name}_{t}"
-        for name in ("bin_index", "slopes", "slopes_pack", "periodic_knots", "pad_periodic", "pack", "cell_order", "cell_sort", "gather",
+        for name in ("bin_index", "slopes", "slopes_pack", "periodic_knots", "pad_periodic", "pack", "cell_order", "cell_sort", "gather", "halo_table", "eval_stencil",
                      "gather_multi", "scatter", "vjp_tables", "ppoly_eval", "ppoly_pack", "ppoly_from_hermite",
                      "ppoly_derivative", "ppoly_antiderivative")
         for t in ("f32", "f64")
@@ -92,6 +97,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.ipx_build_info.argtypes = []
     lib.ipx_slopes_workspace_bytes.restype = C.c_size_t
     lib.ipx_slopes_workspace_bytes.argtypes = [i32, i32, i32]
+    lib.ipx_halo_table_elems.restype = C.c_int64
+    lib.ipx_halo_table_elems.argtypes = [i32, C.POINTER(i32), i32, i32]
     lib.ipx_cell_order_workspace_bytes.restype = C.c_size_t
     lib.ipx_cell_order_workspace_bytes.argtypes = [i64]
     lib.ipx_cell_sort_workspace_bytes.restype = C.c_size_t
@@ -110,6 +117,13 @@ def _declare(lib: C.CDLL) -> None:
         f = getattr(lib, f"ipx_bin_index_{t}")
         f.restype = C.c_int
         f.argtypes = [vp, i32, vp, i64, vp, vp]
+        f = getattr(lib, f"ipx_halo_table_{t}")
+        f.restype = C.c_int
+        f.argtypes = [i32, vp, C.POINTER(i32), i32, C.POINTER(vp), vp, vp]
+        f = getattr(lib, f"ipx_eval_stencil_{t}")
+        f.restype = C.c_int
+        f.argtypes = [i32, C.POINTER(vp), i64, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), vp, vp, i32,
+                      C.c_double, i32, C.POINTER(Params), i32, vp, vp, i32, vp, vp]
         f = getattr(lib, f"ipx_slopes_{t}")
         f.restype = C.c_int
         f.argtypes = [vp, i32, vp, i64, i64, i32, C.POINTER(SlopeOpts), vp, vp, vp]

@@ -391,6 +391,61 @@ def _eval_dev(ndim, qs, knots, perms, ns, tables, layout, batch, method_class, p
     return out, idx
 
 
+# methods whose slope chain is a linear three-point stencil along one axis: evaluated straight
+# from f by ipx_eval_stencil_* (no slope tables, no records): name -> slope code
+_STENCIL_METHODS = {"cubic": L.IPX_SLOPE_CUBIC, "cardinal": L.IPX_SLOPE_CARDINAL, "catmull-rom": L.IPX_SLOPE_CARDINAL}
+_STENCIL_SMEM = 227 * 1024 - 4096  # what the knots + coefficients of all axes may take per CTA
+stencil_hint = L.IPX_STENCIL_AUTO  # experiments / benchmarks: force a kernel shape
+
+
+def _stencil_fits(nks, elem) -> bool:
+    """Shared memory the stencil kernels need for the knots and coefficients (st_layout)."""
+    total = sum(((nk * elem + 31) & ~31) + nk * 4 * elem for nk in nks)
+    return total <= _STENCIL_SMEM
+
+
+def _halo_dev(ndim: int, f: torch.Tensor, periodic: list, perms: list, pad_first: bool) -> torch.Tensor:
+    """f -> halo table (ipx_halo_table_*): two extra rows each side of a periodic axis (wrapped;
+    ``pad_first``: the functional form's convention, ghost rows beyond the padded ends), one ghost
+    row each side of an open one."""
+    lib = L.load()
+    ns = [int(f.shape[ax]) for ax in range(ndim)]
+    mask = 0
+    for ax in range(ndim):
+        if periodic[ax]:
+            mask |= L.IPX_PAD_FIRST(ax) if pad_first else L.IPX_PERIODIC(ax)
+    narr = (C.c_int32 * ndim)(*ns)
+    elems = int(lib.ipx_halo_table_elems(ndim, narr, mask, f.element_size()))
+    errorif(elems <= 0, RuntimeError, "ipx_halo_table_elems failed")
+    out = torch.empty(elems, dtype=f.dtype, device=f.device)
+    fn = getattr(lib, f"ipx_halo_table_{_suffix(f)}")
+    L.check(fn(ndim, _ptr(f), narr, mask, _ptr_array(list(perms)), _ptr(out), _stream()), "ipx_halo_table")
+    return out
+
+
+def _eval_stencil_dev(ndim, qs, knots, sknots, ns, halo, code, c, mask, params, return_index=False, out=None,
+                      records=None):
+    """One call into ipx_eval_stencil_* on the current stream; returns None if the C ABI says
+    IPX_EUNSUPPORTED (knot vectors too long for shared memory).  ``records``: the packed records
+    of the same tables, if the caller has them (the device then picks the faster form per stream)."""
+    lib = L.load()
+    nq = qs[0].numel()
+    dt = qs[0].dtype
+    dev = qs[0].device
+    if out is None:
+        out = torch.empty((nq, 1), dtype=dt, device=dev)
+    idx = torch.empty((ndim, nq), dtype=torch.int32, device=dev) if return_index else None
+    ws = torch.empty(4, dtype=torch.int32, device=dev) if stencil_hint == L.IPX_STENCIL_AUTO else None
+    fn = getattr(lib, f"ipx_eval_stencil_{_suffix(qs[0])}")
+    narr = (C.c_int32 * ndim)(*[int(n) for n in ns])
+    rc = fn(ndim, _ptr_array(qs), nq, _ptr_array(knots), _ptr_array(sknots), narr, _ptr(halo), _ptr(records), code,
+            float(c), mask, C.byref(params), 0, _ptr(out), _ptr(idx), stencil_hint, _ptr(ws), _stream())
+    if rc == L.IPX_EUNSUPPORTED:
+        return None
+    L.check(rc, "ipx_eval_stencil")
+    return out, idx
+
+
 # --------------------------------------------------------------------------- host <-> device streaming
 # Queries that live in host memory (NumPy arrays, CPU tensors) are streamed through the GPU in
 # chunks on a few CUDA streams, so the H2D copy of chunk c+1, the kernel of chunk c and the
@@ -592,6 +647,43 @@ def _interp(ndim, qs, knots, f, method, derivative, extrap, period, kwargs, retu
     perms = [None] * ndim
     kuse = list(kn)
     packed = None
+    params = _make_params(ndim, derivs, ex, periods)
+    if (method in _STENCIL_METHODS and batch == 1 and not io.complex
+            and all(tabs[n] is None for n in names[1:])
+            and _stencil_fits([kn[ax].shape[0] + (2 if pk[ax] is not None else 0) for ax in range(ndim)],
+                              kn[0].element_size())):
+        # linear three-point stencils: evaluate straight from f.  The functional form takes its
+        # slopes on the PADDED knots (_spline.py:924-938 precede :1027-1040): IPX_PAD_FIRST.
+        per = [p is not None for p in pk]
+        halo = _halo_dev(ndim, tabs["f"], per, [p[1] if p is not None else None for p in pk], True)
+        sk = [pk[ax][0] if per[ax] else kn[ax] for ax in range(ndim)]
+        smask = sum(L.IPX_PAD_FIRST(ax) for ax in range(ndim) if per[ax])
+        sns = [tabs["f"].shape[ax] for ax in range(ndim)]
+        code = _STENCIL_METHODS[method]
+        cten = float(kwargs.get("c", 0)) if method == "cardinal" else 0.0
+        # several queries per cell: the records of the (padded) table as well, one fused pass; the
+        # device then picks the faster form for the stream it sees (dense cell-sorted 3-D streams)
+        recs = None
+        nq_total = int(np.prod([int(v) for v in np.broadcast_shapes(*[_shape(q) for q in qs])], dtype=np.int64))
+        cells = float(np.prod([max(1, int(k.shape[0]) - 1) for k in sk], dtype=np.float64))
+        if ndim >= 2 and nq_total >= 3.0 * cells and nq_total >= (1 << 16):
+            ftab = tabs["f"]
+            for ax in range(ndim):
+                if per[ax]:
+                    ftab = _pad_periodic_dev(ftab, ax, pk[ax][1])
+            recs = _slopes_pack_dev(ndim, sk, ftab, 1, method, kwargs)
+
+        def launch_st(dq, dout, want_idx):
+            res = _eval_stencil_dev(ndim, dq, sk, [None] * ndim, sns, halo, code, cten, smask, params,
+                                    want_idx, dout, recs)
+            errorif(res is None, RuntimeError, "ipx_eval_stencil: unsupported")
+            return res
+
+        if presort:
+            # the cell sort sees the padded knots as they are: wrap-only axes of padded extent
+            launch_st = _presorted(launch_st, ndim, sk, [n + (2 if per[ax] else 0) for ax, n in enumerate(sns)],
+                                   sum(L.IPX_WRAP_ONLY(ax) for ax in range(ndim) if per[ax]), params, batch)
+        return _execute(io, qs, launch_st, batch, fshape_user[ndim:], out_arg, return_index)
     if mclass == L.IPX_CUBIC:
         missing = [n for n in names[1:] if tabs[n] is None]
         if missing and any(p is not None for p in pk):
@@ -629,7 +721,6 @@ def _interp(ndim, qs, knots, f, method, derivative, extrap, period, kwargs, retu
         tables = [tabs["f"]]
 
     ns = [tabs["f"].shape[ax] for ax in range(ndim)]
-    params = _make_params(ndim, derivs, ex, periods)
 
     # Many queries on scalar-valued cubic tables: interleave the tables once (one pass over
     # them) and use the tile kernel, as Interpolator* does; few queries: read the reference's
@@ -832,19 +923,48 @@ class _InterpolatorND:
         self._io = io
         self._fshape = fshape
         self._knots = kn
-        tabs = {"f": io.table(f)}
-        self._batch = int(np.prod(tabs["f"].shape[ndim:], dtype=np.int64))
+        self._f = io.table(f)
+        self._given = {n: None if given[n] is None else io.table(given[n]) for n in names[1:]}
+        self._kwargs = kwargs
+        self._batch = int(np.prod(self._f.shape[ndim:], dtype=np.int64))
         self._pk_cache = {}
         self._packed = None
-        if all(v is None for v in given.values()):
+        self._tabs = None
+        self._halo = None
+        if (method in _STENCIL_METHODS and self._batch == 1 and not io.complex
+                and all(v is None for v in given.values())):
+            # linear three-point stencils on a scalar table: evaluate straight from f (one padded
+            # copy of f instead of 2^d slope tables); `.derivs` and the packed records are built
+            # only if somebody asks for them
+            periods = _parse_ndarg(period, ndim)
+            pk = [self._periodic(ax, periods[ax]) if periods[ax] is not None else None for ax in range(ndim)]
+            per = [p is not None for p in pk]
+            # knots that are not sorted inside one period put the one-sided end stencils in the
+            # middle of the sorted table: such tables keep the record form
+            if all(p is None or p[1] is None for p in pk) and _stencil_fits(
+                    [kn[ax].shape[0] + (2 if per[ax] else 0) for ax in range(ndim)], kn[0].element_size()):
+                self._halo = _halo_dev(ndim, self._f, per, [None] * ndim, False)
+                if ndim == 1:
+                    return  # (2-D / 3-D keep the records as well: the faster form depends on the stream)
+        self._build_records()
+
+    def _build_records(self):
+        """Slope tables on the UN-padded grid (_spline.py:380-393) and, for the cubic family, the
+        packed records the tile kernel streams."""
+        if self._tabs is not None:
+            return
+        ndim = self._ndim
+        names = TABLES[ndim]
+        kn, io, method, kwargs = self._knots, self._io, self.method, self._kwargs
+        if all(v is None for v in self._given.values()):
             # nothing supplied: one fused pass f -> packed records; the separate slope tables
             # (`.derivs`) are split off the records only if somebody asks for them
-            self._packed = _slopes_pack_dev(ndim, kn, tabs["f"], self._batch, method, kwargs)
+            self._packed = _slopes_pack_dev(ndim, kn, self._f, self._batch, method, kwargs)
         if self._packed is not None:
-            self._tabs = _RecordTables(names, tabs["f"], self._packed)
+            self._tabs = _RecordTables(names, self._f, self._packed)
             return
-        for n in names[1:]:
-            tabs[n] = None if given[n] is None else io.table(given[n])
+        tabs = {"f": self._f}
+        tabs.update(self._given)
         for name, src, ax in CHAIN[ndim]:
             if tabs[name] is None:
                 tabs[name] = _slopes_dev(kn[ax], tabs[src], method, ax, kwargs, io.complex)
@@ -855,10 +975,11 @@ class _InterpolatorND:
     # the reference exposes these as pytree leaves
     @property
     def f(self):
-        return self._user(self._tabs["f"])
+        return self._user(self._f)
 
     @property
     def derivs(self):
+        self._build_records()
         return {n: self._user(self._tabs[n]) for n in TABLES[self._ndim][1:]}
 
     def _user(self, t):
@@ -887,12 +1008,13 @@ class _InterpolatorND:
         if io.rdt != st.rdt:
             # queries wider than the stored tables: use the functional form, which promotes
             # everything exactly as the reference does
+            self._build_records()
             kw = {n: self._user(self._tabs[n]) for n in TABLES[ndim][1:]}
             if out is not None:
                 kw["out"] = out
             if presort:
                 kw["presort"] = True
-            res = _interp(ndim, qs, [k for k in self._knots], self._user(self._tabs["f"]),
+            res = _interp(ndim, qs, [k for k in self._knots], self._user(self._f),
                           self.method, derivative, self.extrap, self.period, kw, return_index)
             if io.want_torch:
                 return res
@@ -909,17 +1031,29 @@ class _InterpolatorND:
                 kuse[ax], perms[ax] = self._periodic(ax, periods[ax])
                 mask |= L.IPX_PERIODIC(ax)
         mclass = _method_class(self.method)
-        if mclass == L.IPX_CUBIC:
-            tables, layout = [self._packed], L.IPX_AOS
-        else:
-            tables, layout = [self._tabs["f"]], L.IPX_SOA
-        ns = [self._tabs["f"].shape[ax] for ax in range(ndim)]
+        ns = [self._f.shape[ax] for ax in range(ndim)]
         params = _make_params(ndim, derivs, ex, periods)
         batch = self._batch
+        state = {}
 
-        def launch(dq, dout, want_idx):
+        def launch_records(dq, dout, want_idx):
+            if "tables" not in state:
+                self._build_records()
+                state["tables"] = ([self._packed], L.IPX_AOS) if mclass == L.IPX_CUBIC else ([self._f], L.IPX_SOA)
+            tables, layout = state["tables"]
             return _eval_dev(ndim, dq, kuse, perms, ns, tables, layout, batch, mclass, mask, params,
                              want_idx, dout)
+
+        def launch(dq, dout, want_idx):
+            if self._halo is not None:
+                # Interpolator* takes its slopes on the un-padded knots, then wraps: IPX_PERIODIC
+                res = _eval_stencil_dev(ndim, dq, kuse, self._knots, ns, self._halo, _STENCIL_METHODS[self.method],
+                                        float(self._kwargs.get("c", 0)) if self.method == "cardinal" else 0.0,
+                                        mask, params, want_idx, dout, self._packed)
+                if res is not None:
+                    return res
+                self._halo = None  # knot vectors too long for shared memory: record form from now on
+            return launch_records(dq, dout, want_idx)
 
         if presort:
             launch = _presorted(launch, ndim, kuse, ns, mask, params, batch)

@@ -228,6 +228,59 @@ __device__ __forceinline__ void linear_weights(const AxisLoc<T>& L, int order, T
 }
 
 // ------------------------------------------------------------------------------------
+// pieces shared by the warp-cooperative kernels (ipx_eval_tile.cuh, ipx_stencil.cu)
+// ------------------------------------------------------------------------------------
+// rare paths kept out of line (values in and out through registers only): the hot loop must
+// stay small for the instruction caches
+template <typename T> __device__ __noinline__ T py_mod_slow(T q, T P) { return py_mod(q, P); }
+template <typename T>
+__device__ __noinline__ int bin_index_slow(const T* x, int n, T q, T x_first, T inv_h) {
+  T lo, hi;
+  return bin_index(x, n, q, x_first, inv_h, lo, hi);
+}
+
+// One-period wrap of a query: r = q + P for q in [-P, 0), q - P for q in [P, 2P) (exact, Sterbenz),
+// q for q in [0, P) -- what the Python remainder gives there.  `bad` = anything else (|q| beyond one
+// period, NaN, -0.0, a sum that rounds up to P): the caller repairs those with the out-of-line
+// fmod.  Signs are tested on the integer pipe (q - P >= 0 <=> q >= P exactly), which leaves one
+// add and one compare on the FP64 pipe that bounds the kernel.
+__device__ __forceinline__ int sign_word(double v) { return __double2hiint(v); }
+__device__ __forceinline__ int sign_word(float v) { return __float_as_int(v); }
+template <typename T> __device__ __forceinline__ T wrap_one_period(T v, T Pd, bool& bad) {
+  const bool neg = sign_word(v) < 0;
+  const T s = v + (neg ? Pd : -Pd);
+  const bool s_neg = sign_word(s) < 0;
+  const T r = (neg || !s_neg) ? s : v;
+  bad = (neg && s_neg) || !(r < Pd);
+  return r;
+}
+
+// cubic Hermite weights from the local coordinate pieces (same formulas as hermite_weights)
+template <typename T, bool ORD0>
+__device__ __forceinline__ void hermite_weights_r(T q, T x0, T x1, int order, T dxi, T w[4]) {
+  T dx = x1 - x0;
+  T t = (q - x0) * dxi;
+  T tt0, tt1, tt2, tt3;
+  if (ORD0 || order <= 0) {
+    tt0 = T(1); tt1 = t; tt2 = t * t; tt3 = tt2 * t;
+  } else if (order == 1) {
+    tt0 = T(0); tt1 = dxi; tt2 = (T(2) * t) * dxi; tt3 = (T(3) * (t * t)) * dxi;
+  } else if (order == 2) {
+    T s = dxi * dxi;
+    tt0 = T(0); tt1 = T(0); tt2 = T(2) * s; tt3 = (T(6) * t) * s;
+  } else if (order == 3) {
+    tt0 = T(0); tt1 = T(0); tt2 = T(0); tt3 = T(6) * (dxi * dxi * dxi);
+  } else {
+    T z = dxi * T(0);
+    tt0 = z; tt1 = z; tt2 = z; tt3 = z;
+  }
+  w[0] = tt0 - T(3) * tt2 + T(2) * tt3;
+  w[1] = T(3) * tt2 - T(2) * tt3;
+  w[2] = (tt1 - T(2) * tt2 + tt3) * dx;
+  w[3] = (tt3 - tt2) * dx;
+}
+
+// ------------------------------------------------------------------------------------
 // global loads.  Tables are read-only for the lifetime of a call: use the non-coherent
 // path; 128-bit where the record layout allows it.
 // ------------------------------------------------------------------------------------

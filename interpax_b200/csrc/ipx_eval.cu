@@ -18,11 +18,14 @@
 
 #include "ipx_contract.cuh"
 #include "ipx_device.cuh"
+#include "ipx_internal.cuh"
 
 #define IPX_STR2(x) #x
 #define IPX_STR(x) IPX_STR2(x)
 
 namespace ipx {
+
+thread_local RunIf g_run_if = {nullptr, 0u};
 
 constexpr int kThreads = 256;
 
@@ -35,7 +38,13 @@ template <typename T, int ND> struct EvalArgs {
   int64_t batch;
   ipx_params hp;          // host copy of the traced operands ...
   const ipx_params* dp;   // ... or a device pointer to them (takes precedence)
+  const int32_t* __restrict__ run_flag;  // NULL, or: run only if bit *run_flag of run_accept is set
+  uint32_t run_accept;                   // (ipx_internal.cuh)
 };
+
+template <typename T, int ND> __device__ __forceinline__ bool skip_launch(const EvalArgs<T, ND>& a) {
+  return a.run_flag != nullptr && ((a.run_accept >> (*a.run_flag & 31)) & 1u) == 0;
+}
 
 // linear node index of corner (c0[,c1[,c2]]) times batch
 template <typename T, int ND>
@@ -228,6 +237,7 @@ __global__ void __launch_bounds__(kThreads) eval_kernel(const EvalArgs<T, ND> a,
   constexpr int U = QueriesPerRound<ND>::value;
   __shared__ AxisConst<T> consts[ND];
   __shared__ ipx_params params_s;
+  if (skip_launch(a)) return;
   if (threadIdx.x < ND) axis_consts(a.ax[threadIdx.x], consts[threadIdx.x]);
   if (threadIdx.x == 32) params_s = a.dp ? *a.dp : a.hp;
   __syncthreads();
@@ -399,6 +409,9 @@ static int launch_eval(const T* const* q, int64_t nq, const T* const* knots,
     a.dp = nullptr;
     a.hp = *params;
   }
+  a.run_flag = g_run_if.flag;
+  a.run_accept = g_run_if.accept;
+  g_run_if = RunIf{nullptr, 0u};
 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int bpad_log2 = 0;  // lanes per query = smallest power of two >= min(batch, 32)

@@ -44,6 +44,7 @@ template <> __device__ __forceinline__ double shfl_t<double>(double v, int src) 
 // METHOD: IPX_CUBIC (tables f, fx; AoS or SoA) or IPX_LINEAR (table f)
 template <typename T, int METHOD, int LAYOUT>
 __global__ void __launch_bounds__(kRowThreads) eval1d_rows_kernel(const EvalArgs<T, 1> a) {
+  if (skip_launch(a)) return;
   __shared__ AxisConst<T> consts;
   __shared__ ipx_params params_s;
   if (threadIdx.x == 0) axis_consts(a.ax[0], consts);

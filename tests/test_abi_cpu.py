@@ -31,7 +31,7 @@ def header_symbols():
     for d in (1, 2, 3):
         for t in ("f32", "f64"):
             out.add(f"ipx_eval{d}d_{t}")
-    return {n for n in out if not n.startswith("ipx_eval") or re.fullmatch(r"ipx_eval[123]d_f(32|64)", n)}
+    return {n for n in out if not n.startswith("ipx_eval") or re.fullmatch(r"ipx_eval([123]d|_stencil)_f(32|64)", n)}
 
 
 def test_library_exports_every_declared_symbol():

@@ -214,6 +214,7 @@ def test_fused_slopes_pack_is_bitwise_the_table_chain(method, dtype):
         # the class builds from the fused records and splits `.derivs` off them on demand
         cls = ipx.Interpolator2D if ndim == 2 else ipx.Interpolator3D
         obj = cls(*kd, fd, method=method, **kw)
+        obj._build_records()  # (scalar cubic / cardinal tables evaluate from f and build these lazily)
         assert isinstance(obj._tabs, api._RecordTables)
         for name in api.TABLES[ndim][1:]:
             assert torch.equal(obj.derivs[name], tabs[name]), (method, shape, name)
@@ -233,6 +234,7 @@ def test_fused_slopes_pack_unsupported_cases_use_the_table_chain():
     x, y = np.linspace(0, 1, 2), np.linspace(0, 1, 7)
     f = rng.normal(size=(2, 7))
     obj = ipx.Interpolator2D(x, y, f, method="cubic")          # an axis with two knots
+    obj._build_records()
     assert not isinstance(obj._tabs, api._RecordTables)
     obj = ipx.Interpolator2D(y, y, rng.normal(size=(7, 7)), method="akima")
     assert not isinstance(obj._tabs, api._RecordTables)
@@ -798,7 +800,8 @@ def test_cubic2_long_axis_windowed_solve(dtype):
 def test_presort_is_bitwise_identical(ndim):
     """presort=True (cell-order radix sort -> gather -> evaluate -> scatter) must give exactly
     the results of the plain call, in the caller's order, for every method class, with
-    periodic axes, extrapolation fills, NaN queries, batches, and from host memory."""
+    periodic axes, extrapolation fills, NaN queries, batches, and from host memory (scalar cubic
+    tables: to rounding, see below)."""
     rng = np.random.default_rng(60 + ndim)
     dev = torch.device("cuda")
     ns = [37, 29, 23][:ndim]
@@ -818,7 +821,12 @@ def test_presort_is_bitwise_identical(ndim):
             b = ip(*qs, presort=True)
             assert np.array_equal(np.isnan(a), np.isnan(b))
             m = ~np.isnan(a)
-            assert np.array_equal(a[m], b[m]), (method, batch_shape)
+            if method == "cubic" and batch_shape == ():
+                # scalar cubic tables have two forms (evaluation from f, packed records) and the
+                # device picks one per stream (random order vs cell-sorted): equal to rounding
+                np.testing.assert_allclose(a[m], b[m], rtol=1e-13, atol=1e-13 * np.abs(a[m]).max())
+            else:
+                assert np.array_equal(a[m], b[m]), (method, batch_shape)
             c = fun(*qs, *knots, f, method, 0, extrap, per, presort=True)
             assert_parity(c, fun(*qs, *knots, f, method, 0, extrap, per), method)
     # the order really is the cell order
