@@ -93,6 +93,10 @@ typedef struct ipx_slope_opts {
 int ipx_version(void);
 /* Static description of the build: "sm_100a" etc.  Never NULL. */
 const char* ipx_build_info(void);
+/* Diagnostics: kernels enqueued so far by this process through the evaluation entry points
+ * (ipx_eval*, ipx_eval_stencil_*, ipx_halo_table_*), skipped candidates of the device-side
+ * choice included.  The one counter in the library; it influences nothing. */
+uint64_t ipx_launch_count(void);
 
 /* ---------------------------------------------------------------------------------
  * Query evaluation.  Replaces the bodies of

@@ -64,7 +64,7 @@ class SlopeOpts(C.Structure):
 # every symbol include/ipx.h declares; tests/test_abi.py checks the .so exports them all
 SYMBOLS = (
     ["ipx_version", "ipx_build_info", "ipx_slopes_workspace_bytes", "ipx_cell_order_workspace_bytes",
-     "ipx_cell_sort_workspace_bytes", "ipx_halo_table_elems"]
+     "ipx_cell_sort_workspace_bytes", "ipx_halo_table_elems", "ipx_launch_count"]
     + [f"ipx_eval{d}d_{t}" for d in (1, 2, 3) for t in ("f32", "f64")]
     + [
         f"ipx_{name}_{t}"
@@ -97,6 +97,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.ipx_build_info.argtypes = []
     lib.ipx_slopes_workspace_bytes.restype = C.c_size_t
     lib.ipx_slopes_workspace_bytes.argtypes = [i32, i32, i32]
+    lib.ipx_launch_count.restype = C.c_uint64
+    lib.ipx_launch_count.argtypes = []
     lib.ipx_halo_table_elems.restype = C.c_int64
     lib.ipx_halo_table_elems.argtypes = [i32, C.POINTER(i32), i32, i32]
     lib.ipx_cell_order_workspace_bytes.restype = C.c_size_t

@@ -16,6 +16,8 @@
 // (64 + 16 + 4 FMAs in 3-D instead of 4096 + 64).
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include "ipx_contract.cuh"
 #include "ipx_device.cuh"
 #include "ipx_internal.cuh"
@@ -26,6 +28,8 @@
 namespace ipx {
 
 thread_local RunIf g_run_if = {nullptr, 0u};
+static std::atomic<unsigned long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 constexpr int kThreads = 256;
 
@@ -419,8 +423,10 @@ static int launch_eval(const T* const* q, int64_t nq, const T* const* knots,
   int grid = grid_for(((nq << bpad_log2) + QueriesPerRound<ND>::value - 1) / QueriesPerRound<ND>::value, kThreads);
   if constexpr (ND == 1) {
     // wide vector-valued 1-D tables: the row-streaming kernel
-    if (launch_rows<T>(a, method, layout, s))
+    if (launch_rows<T>(a, method, layout, s)) {
+      count_launches(1);
       return cudaPeekAtLastError() == cudaSuccess ? IPX_OK : IPX_ELAUNCH;
+    }
   }
   if (method == IPX_CUBIC) {
     if (layout == IPX_AOS) {
@@ -433,6 +439,7 @@ static int launch_eval(const T* const* q, int64_t nq, const T* const* knots,
   } else {
     eval_kernel<T, ND, IPX_NEAREST, IPX_SOA><<<grid, kThreads, 0, s>>>(a, bpad_log2);
   }
+  count_launches(1);
   return cudaPeekAtLastError() == cudaSuccess ? IPX_OK : IPX_ELAUNCH;
 }
 
@@ -507,6 +514,7 @@ extern "C" int ipx_bin_index_f64(const double* knots, int32_t n, const double* q
 }
 
 extern "C" int ipx_version(void) { return IPX_VERSION; }
+extern "C" uint64_t ipx_launch_count(void) { return ipx::g_launches.load(std::memory_order_relaxed); }
 extern "C" const char* ipx_build_info(void) {
   return "libipx " __DATE__ " nvcc " IPX_STR(__CUDACC_VER_MAJOR__) "." IPX_STR(
       __CUDACC_VER_MINOR__) " arch sm_100a";

@@ -15,4 +15,8 @@ struct RunIf {
 };
 extern thread_local RunIf g_run_if;
 
+// Diagnostics only: kernels enqueued by this process through the evaluation entry points
+// (ipx_launch_count), so a benchmark can report how many launches its timed region made.
+void count_launches(int n);
+
 }  // namespace ipx

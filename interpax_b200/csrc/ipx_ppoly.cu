@@ -14,6 +14,7 @@
 #include <math_constants.h>
 
 #include "ipx_device.cuh"
+#include "ipx_internal.cuh"
 
 namespace ipx {
 
@@ -258,11 +259,11 @@ static int launch_ppoly_eval(const T* c, int32_t layout, int32_t k, int32_t m, i
   a.sj = layout == IPX_AOS ? 1 : (int64_t)m * batch;
   a.si = layout == IPX_AOS ? k : batch;
   if (batch == 1) {
-    ppoly_eval_scalar_kernel<T><<<poly_grid((nq + kPolyUnroll - 1) / kPolyUnroll), kPolyThreads, 0, s>>>(a);
+    ppoly_eval_scalar_kernel<T><<<poly_grid((nq + kPolyUnroll - 1) / kPolyUnroll), kPolyThreads, 0, s>>>(a); count_launches(1);
   } else if (batch >= 16) {
-    ppoly_eval_rows_kernel<T><<<poly_grid(nq * 32), kPolyThreads, 0, s>>>(a);
+    ppoly_eval_rows_kernel<T><<<poly_grid(nq * 32), kPolyThreads, 0, s>>>(a); count_launches(1);
   } else {
-    ppoly_eval_elem_kernel<T><<<poly_grid(nq * batch), kPolyThreads, 0, s>>>(a);
+    ppoly_eval_elem_kernel<T><<<poly_grid(nq * batch), kPolyThreads, 0, s>>>(a); count_launches(1);
   }
   return cudaPeekAtLastError() == cudaSuccess ? IPX_OK : IPX_ELAUNCH;
 }
@@ -272,7 +273,7 @@ static int launch_ppoly_pack(const T* c, int32_t k, int32_t m, T* out, void* str
   if (k < 1 || m < 1) return IPX_EINVAL;
   if (c == nullptr || out == nullptr) return IPX_EINVAL;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  ppoly_pack_kernel<T><<<poly_grid((int64_t)k * m), kPolyThreads, 0, s>>>(c, k, m, out);
+  ppoly_pack_kernel<T><<<poly_grid((int64_t)k * m), kPolyThreads, 0, s>>>(c, k, m, out); count_launches(1);
   return cudaPeekAtLastError() == cudaSuccess ? IPX_OK : IPX_ELAUNCH;
 }
 
@@ -283,7 +284,7 @@ static int launch_from_hermite(const T* x, int32_t n, const T* y, const T* dydx,
   if (batch == 0) return IPX_OK;
   if (x == nullptr || y == nullptr || dydx == nullptr || c == nullptr) return IPX_EINVAL;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  hermite_to_ppoly_kernel<T><<<poly_grid((int64_t)(n - 1) * batch), kPolyThreads, 0, s>>>(x, n, y, dydx, batch, c);
+  hermite_to_ppoly_kernel<T><<<poly_grid((int64_t)(n - 1) * batch), kPolyThreads, 0, s>>>(x, n, y, dydx, batch, c); count_launches(1);
   return cudaPeekAtLastError() == cudaSuccess ? IPX_OK : IPX_ELAUNCH;
 }
 
@@ -295,7 +296,7 @@ static int launch_ppoly_derivative(const T* c, int32_t k, int32_t m, int64_t bat
   if (c == nullptr || c2 == nullptr) return IPX_EINVAL;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t per = (int64_t)m * batch;
-  ppoly_derivative_kernel<T><<<poly_grid((int64_t)(k - nu) * per), kPolyThreads, 0, s>>>(c, k, per, nu, c2);
+  ppoly_derivative_kernel<T><<<poly_grid((int64_t)(k - nu) * per), kPolyThreads, 0, s>>>(c, k, per, nu, c2); count_launches(1);
   return cudaPeekAtLastError() == cudaSuccess ? IPX_OK : IPX_ELAUNCH;
 }
 
@@ -306,8 +307,8 @@ static int launch_ppoly_antiderivative(const T* c, int32_t k, int32_t m, int64_t
   if (batch == 0) return IPX_OK;
   if (c == nullptr || x == nullptr || c2 == nullptr) return IPX_EINVAL;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  ppoly_polyint_kernel<T><<<poly_grid((int64_t)m * batch), kPolyThreads, 0, s>>>(c, k, m, batch, x, c2);
-  ppoly_continuity_kernel<T><<<poly_grid(batch), kPolyThreads, 0, s>>>(k, m, batch, c2);
+  ppoly_polyint_kernel<T><<<poly_grid((int64_t)m * batch), kPolyThreads, 0, s>>>(c, k, m, batch, x, c2); count_launches(1);
+  ppoly_continuity_kernel<T><<<poly_grid(batch), kPolyThreads, 0, s>>>(k, m, batch, c2); count_launches(1);
   return cudaPeekAtLastError() == cudaSuccess ? IPX_OK : IPX_ELAUNCH;
 }
 

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include "ipx_device.cuh"
+#include "ipx_internal.cuh"
 
 namespace ipx {
 
@@ -134,9 +135,9 @@ static int launch_periodic_knots(const T* x, int32_t n, double period, T* xpad, 
   T* xm = static_cast<T*>(workspace);
   int* counters = reinterpret_cast<int*>(xm + n + ((n & 1) ? 1 : 0));  // keep 8-byte alignment
   T P = T(period < 0 ? -period : period);
-  zero_counters_kernel<<<1, 1, 0, s>>>(counters);
-  wrap_knots_kernel<T><<<prep_grid(n), kPrepThreads, 0, s>>>(x, n, P, xm, counters);
-  rank_knots_kernel<T><<<prep_grid(n), kPrepThreads, 0, s>>>(xm, n, P, counters, xpad, perm);
+  zero_counters_kernel<<<1, 1, 0, s>>>(counters); count_launches(1);
+  wrap_knots_kernel<T><<<prep_grid(n), kPrepThreads, 0, s>>>(x, n, P, xm, counters); count_launches(1);
+  rank_knots_kernel<T><<<prep_grid(n), kPrepThreads, 0, s>>>(xm, n, P, counters, xpad, perm); count_launches(1);
   return cudaPeekAtLastError() == cudaSuccess ? IPX_OK : IPX_ELAUNCH;
 }
 
@@ -147,7 +148,7 @@ static int launch_pad(const T* in, int64_t outer, int32_t n, int64_t inner, cons
   if (outer * inner == 0) return IPX_OK;
   if (in == nullptr || out == nullptr) return IPX_EINVAL;
   pad_periodic_kernel<T><<<prep_grid(outer * (n + 2) * inner), kPrepThreads, 0,
-                           static_cast<cudaStream_t>(stream)>>>(in, outer, n, inner, perm, out);
+                           static_cast<cudaStream_t>(stream)>>>(in, outer, n, inner, perm, out); count_launches(1);
   return cudaPeekAtLastError() == cudaSuccess ? IPX_OK : IPX_ELAUNCH;
 }
 
@@ -170,7 +171,7 @@ static int launch_pack_n(int ndim, const T* const* tables, int64_t total, T* out
     if (tables[ff] == nullptr) return IPX_EINVAL;
     a.tab[pack_slot(ndim, ff)] = tables[ff];
   }
-  pack_kernel<T, NT><<<prep_grid(total * NT), kPrepThreads, 0, s>>>(a, total, out);
+  pack_kernel<T, NT><<<prep_grid(total * NT), kPrepThreads, 0, s>>>(a, total, out); count_launches(1);
   return cudaPeekAtLastError() == cudaSuccess ? IPX_OK : IPX_ELAUNCH;
 }
 

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include "ipx_device.cuh"
+#include "ipx_internal.cuh"
 
 namespace ipx {
 
@@ -586,38 +587,38 @@ static int launch_slopes(const T* x, int32_t n, const T* f, int64_t outer, int64
   const int grid = slope_grid(total);
   switch (method) {
     case IPX_SLOPE_ZERO:
-      fill_zero_kernel<T><<<grid, kSlopeThreads, 0, s>>>(out, total);
+      fill_zero_kernel<T><<<grid, kSlopeThreads, 0, s>>>(out, total); count_launches(1);
       break;
     case IPX_SLOPE_CUBIC:
       if (n < 2) return IPX_EINVAL;
-      slopes_cubic_kernel<T><<<grid, kSlopeThreads, 0, s>>>(a);
+      slopes_cubic_kernel<T><<<grid, kSlopeThreads, 0, s>>>(a); count_launches(1);
       break;
     case IPX_SLOPE_CARDINAL: {
       if (n < 2) return IPX_EINVAL;
       T c = opts ? T(opts->c) : T(0);
-      slopes_cardinal_kernel<T><<<grid, kSlopeThreads, 0, s>>>(a, T(1) - c);
+      slopes_cardinal_kernel<T><<<grid, kSlopeThreads, 0, s>>>(a, T(1) - c); count_launches(1);
       break;
     }
     case IPX_SLOPE_MONOTONIC:
     case IPX_SLOPE_MONOTONIC0:
       if (n < 2) return IPX_EINVAL;
-      slopes_monotonic_kernel<T><<<grid, kSlopeThreads, 0, s>>>(a, method == IPX_SLOPE_MONOTONIC0);
+      slopes_monotonic_kernel<T><<<grid, kSlopeThreads, 0, s>>>(a, method == IPX_SLOPE_MONOTONIC0); count_launches(1);
       break;
     case IPX_SLOPE_AKIMA: {
       if (n < 2 || workspace == nullptr) return IPX_EINVAL;
       T* gmax = static_cast<T*>(workspace);
-      akima_init_kernel<T><<<1, 1, 0, s>>>(gmax);
-      akima_max_kernel<T><<<grid, kSlopeThreads, 0, s>>>(a, gmax);
-      slopes_akima_kernel<T><<<grid, kSlopeThreads, 0, s>>>(a, gmax);
+      akima_init_kernel<T><<<1, 1, 0, s>>>(gmax); count_launches(1);
+      akima_max_kernel<T><<<grid, kSlopeThreads, 0, s>>>(a, gmax); count_launches(1);
+      slopes_akima_kernel<T><<<grid, kSlopeThreads, 0, s>>>(a, gmax); count_launches(1);
       break;
     }
     case IPX_SLOPE_AKIMA_COMPLEX: {
       if (n < 2 || workspace == nullptr || (inner & 1) != 0) return IPX_EINVAL;
       T* gmax = static_cast<T*>(workspace);
       const int cgrid = slope_grid(total / 2);
-      akima_init_kernel<T><<<1, 1, 0, s>>>(gmax);
-      akima_max_complex_kernel<T><<<cgrid, kSlopeThreads, 0, s>>>(a, gmax);
-      slopes_akima_complex_kernel<T><<<cgrid, kSlopeThreads, 0, s>>>(a, gmax);
+      akima_init_kernel<T><<<1, 1, 0, s>>>(gmax); count_launches(1);
+      akima_max_complex_kernel<T><<<cgrid, kSlopeThreads, 0, s>>>(a, gmax); count_launches(1);
+      slopes_akima_complex_kernel<T><<<cgrid, kSlopeThreads, 0, s>>>(a, gmax); count_launches(1);
       break;
     }
     case IPX_SLOPE_CUBIC2: {
@@ -630,17 +631,17 @@ static int launch_slopes(const T* x, int32_t n, const T* f, int64_t outer, int64
       if (bc.start < 0 || bc.start > 2 || bc.end < 0 || bc.end > 2) return IPX_EINVAL;
       const int cgrid = slope_grid(outer * inner);
       if (n == 2 || (n == 3 && bc.start == IPX_BC_NOT_A_KNOT && bc.end == IPX_BC_NOT_A_KNOT)) {
-        cubic2_small_kernel<T><<<cgrid, kSlopeThreads, 0, s>>>(a, bc);
+        cubic2_small_kernel<T><<<cgrid, kSlopeThreads, 0, s>>>(a, bc); count_launches(1);
       } else {
         if (workspace == nullptr) return IPX_EINVAL;
         T* ws = static_cast<T*>(workspace);
         if (n > 4 * kChunk) {
           const int chunks = (n + kChunk - 1) / kChunk;
-          cubic2_wfactor_kernel<T><<<(chunks + 127) / 128, 128, 0, s>>>(x, n, bc.start, bc.end, ws);
-          cubic2_wsolve_kernel<T><<<slope_grid(outer * inner * chunks), kSlopeThreads, 0, s>>>(a, bc, ws);
+          cubic2_wfactor_kernel<T><<<(chunks + 127) / 128, 128, 0, s>>>(x, n, bc.start, bc.end, ws); count_launches(1);
+          cubic2_wsolve_kernel<T><<<slope_grid(outer * inner * chunks), kSlopeThreads, 0, s>>>(a, bc, ws); count_launches(1);
         } else {
-          cubic2_factor_kernel<T><<<1, 32, 0, s>>>(x, n, bc.start, bc.end, ws);
-          cubic2_solve_kernel<T><<<cgrid, kSlopeThreads, 0, s>>>(a, bc, ws);
+          cubic2_factor_kernel<T><<<1, 32, 0, s>>>(x, n, bc.start, bc.end, ws); count_launches(1);
+          cubic2_solve_kernel<T><<<cgrid, kSlopeThreads, 0, s>>>(a, bc, ws); count_launches(1);
         }
       }
       break;
@@ -980,13 +981,13 @@ static int launch_slopes_pack_m(int32_t ndim, const FusedArgs<T>& a, cudaStream_
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return IPX_ELAUNCH;
-    k<<<grid, kSlopeThreads, smem, s>>>(a);
+    k<<<grid, kSlopeThreads, smem, s>>>(a); count_launches(1);
   } else {
     auto k = slopes_pack3d_kernel<T, METHOD>;
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return IPX_ELAUNCH;
-    k<<<grid, kSlopeThreads, smem, s>>>(a);
+    k<<<grid, kSlopeThreads, smem, s>>>(a); count_launches(1);
   }
   return cudaPeekAtLastError() == cudaSuccess ? IPX_OK : IPX_ELAUNCH;
 }

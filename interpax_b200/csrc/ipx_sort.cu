@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 
 #include "ipx_device.cuh"
+#include "ipx_internal.cuh"
 
 namespace ipx {
 
@@ -329,11 +330,11 @@ static void radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_
   uint32_t *ki = keys_a, *vi = vals_a, *ko = keys_b, *vo = vals_b;
   for (int pass = 0; pass < passes; ++pass) {
     const int shift = pass * kRadixBits;
-    radix_hist_kernel<<<p.nblocks, kSortThreads, 0, s>>>(ki, p.n, shift, hist, p.nblocks);
-    scan_tiles_kernel<<<p.ntiles, kScanThreads, 0, s>>>(hist, p.hist_count, sums);
-    scan_sums_kernel<<<1, kScanThreads, 0, s>>>(sums, p.ntiles);
-    scan_add_kernel<<<p.ntiles, kScanThreads, 0, s>>>(hist, p.hist_count, sums);
-    radix_scatter_kernel<<<p.nblocks, kSortThreads, 0, s>>>(ki, vi, p.n, shift, hist, p.nblocks, ko, vo);
+    radix_hist_kernel<<<p.nblocks, kSortThreads, 0, s>>>(ki, p.n, shift, hist, p.nblocks); count_launches(1);
+    scan_tiles_kernel<<<p.ntiles, kScanThreads, 0, s>>>(hist, p.hist_count, sums); count_launches(1);
+    scan_sums_kernel<<<1, kScanThreads, 0, s>>>(sums, p.ntiles); count_launches(1);
+    scan_add_kernel<<<p.ntiles, kScanThreads, 0, s>>>(hist, p.hist_count, sums); count_launches(1);
+    radix_scatter_kernel<<<p.nblocks, kSortThreads, 0, s>>>(ki, vi, p.n, shift, hist, p.nblocks, ko, vo); count_launches(1);
     uint32_t* t = ki; ki = ko; ko = t;
     t = vi; vi = vo; vo = t;
   }
@@ -387,13 +388,13 @@ static int launch_cell_order(const T* const* q, int64_t nq, const T* const* knot
       if (q_sorted[ax] == nullptr) return IPX_EINVAL;
     recs = reinterpret_cast<T*>(ws + p.total);  // p.total is 256-byte aligned
   }
-  cell_key_kernel<T, ND><<<(int)(need < cap ? need : cap), 256, 0, s>>>(a, keys_a, order, recs);
+  cell_key_kernel<T, ND><<<(int)(need < cap ? need : cap), 256, 0, s>>>(a, keys_a, order, recs); count_launches(1);
   radix_sort_pairs(keys_a, order, keys_b, vals_b, hist, sums, p, bits, s);
   if (q_sorted != nullptr) {
     RecGatherArgs<T, ND> g;
     for (int ax = 0; ax < ND; ++ax) g.dst[ax] = q_sorted[ax];
     int64_t gcap = (int64_t)sm_count() * 32;
-    gather_records_kernel<T, ND><<<(int)(need < gcap ? need : gcap), 256, 0, s>>>(recs, order, nq, g);
+    gather_records_kernel<T, ND><<<(int)(need < gcap ? need : gcap), 256, 0, s>>>(recs, order, nq, g); count_launches(1);
   }
   return cudaPeekAtLastError() == cudaSuccess ? IPX_OK : IPX_ELAUNCH;
 }
@@ -453,7 +454,7 @@ static int launch_gather_multi_n(const T* const* src, const uint32_t* order, int
   }
   int64_t need = (n + 255) / 256;
   int64_t cap = (int64_t)sm_count() * 32;
-  gather_multi_kernel<T, NA><<<(int)(need < cap ? need : cap), 256, 0, s>>>(a, order, n);
+  gather_multi_kernel<T, NA><<<(int)(need < cap ? need : cap), 256, 0, s>>>(a, order, n); count_launches(1);
   return cudaPeekAtLastError() == cudaSuccess ? IPX_OK : IPX_ELAUNCH;
 }
 
@@ -480,6 +481,7 @@ static int launch_permute(const T* src, const uint32_t* order, int64_t n, int64_
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (GATHER) gather_kernel<T><<<grid, 256, 0, s>>>(src, order, n, batch, dst);
   else scatter_kernel<T><<<grid, 256, 0, s>>>(src, order, n, batch, dst);
+  count_launches(1);
   return cudaPeekAtLastError() == cudaSuccess ? IPX_OK : IPX_ELAUNCH;
 }
 

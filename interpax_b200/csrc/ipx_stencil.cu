@@ -1049,6 +1049,7 @@ static int st_launch_q(const StArgs<T, ND>& a, const StDevice& d, cudaStream_t s
   int64_t grid = d.sms;  // persistent: one CTA per SM
   if (need < grid) grid = need;
   kern<<<(int)grid, threads, smem, s>>>(a);
+  count_launches(1);
   const cudaError_t err = cudaPeekAtLastError();
   if (err != cudaSuccess && getenv("IPX_DEBUG") != nullptr)
     fprintf(stderr, "ipx stencil launch (dense %d, %d threads, %zu B shared): %s\n", (int)DENSE, threads, smem,
@@ -1174,6 +1175,7 @@ static int launch_stencil(const T* const* q, int64_t nq, const T* const* knots, 
   const bool rec_quads = records != nullptr && ND == 3 && dense_ok && (double)nq >= 3.0 * cells;
   if (!dense && !rec_random && !rec_quads) return st_launch_q<T, ND, false, 4>(a, d, s);  // one candidate: no probe
   stencil_probe_kernel<T, ND, IPX_STENCIL_TAPS><<<1, 256, 0, s>>>(a, workspace);
+  count_launches(1);
   a.flag = workspace;
   uint32_t sparse_accept = 1u << IPX_STREAM_LOCAL;
   if (!dense && !rec_quads) sparse_accept |= 1u << IPX_STREAM_QUADS;
@@ -1217,6 +1219,7 @@ static int launch_halo_nd(const T* f, const int32_t* n, int32_t periodic_mask, c
   int64_t need = (total + 255) / 256;
   int64_t cap = (int64_t)sms * 16;
   halo_kernel<T, ND><<<(int)(need < cap ? need : cap), 256, 0, s>>>(f, h, total, out);
+  count_launches(1);
   return cudaPeekAtLastError() == cudaSuccess ? IPX_OK : IPX_ELAUNCH;
 }
 

@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 
 #include "ipx_device.cuh"
+#include "ipx_internal.cuh"
 
 namespace ipx {
 
@@ -162,6 +163,7 @@ static int launch_vjp(const T* const* q, int64_t nq, const T* const* knots, cons
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (method == IPX_CUBIC) vjp_tables_kernel<T, ND, IPX_CUBIC><<<grid, kVjpThreads, 0, s>>>(a);
   else vjp_tables_kernel<T, ND, IPX_LINEAR><<<grid, kVjpThreads, 0, s>>>(a);
+  count_launches(1);
   return cudaPeekAtLastError() == cudaSuccess ? IPX_OK : IPX_ELAUNCH;
 }
 

@@ -10,3 +10,32 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+def pytest_collection_modifyitems(config, items):
+    """GPU tests need a CUDA device and libipx.so: skip them (instead of erroring) elsewhere."""
+    import pytest
+
+    try:
+        import torch
+
+        have = torch.cuda.is_available()
+    except Exception:
+        have = False
+    if have:
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (the query path has no CPU fallback)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def pytest_terminal_summary(terminalreporter):
+    """How many float32 elements were accepted because the kernel matched the float64 evaluation
+    although it missed rtol 1e-5 against the float32 oracle (tests/test_gpu_parity.py::assert_parity)."""
+    mod = sys.modules.get("test_gpu_parity")
+    if mod is not None and getattr(mod, "HATCH", None) and mod.HATCH["elements_checked"]:
+        h = mod.HATCH
+        terminalreporter.write_line(
+            f"float32 parity: {h['accepted_via_f64_truth']} of {h['elements_checked']} compared elements "
+            "missed rtol 1e-5 against the float32 oracle but met it against the float64 evaluation")

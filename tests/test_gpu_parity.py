@@ -27,6 +27,9 @@ RTOL = {np.dtype(np.float64): 1e-12, np.dtype(np.float32): 1e-5,
 ALL_METHODS = O.METHODS
 
 
+HATCH = {"elements_checked": 0, "accepted_via_f64_truth": 0}  # reported by conftest at the end of the run
+
+
 def assert_parity(got, want, what="", truth=None):
     """|got - want| <= rtol*|want| + rtol*max|want| element-wise.
 
@@ -34,10 +37,10 @@ def assert_parity(got, want, what="", truth=None):
     float64 on the same float32 inputs.  Far outside the knots the cubic is ill-conditioned
     (weights grow like |t|^3 and cancel) and the float32 ORACLE is itself off by more than
     1e-5; its dense 64x64 form loses more digits than the separable form the kernels use.
-    An element that misses the plain tolerance is therefore still accepted if the kernel is
-    within twice the distance from the float64 truth that the oracle's float32 arithmetic
-    reaches at its worst on the same query set -- i.e. the difference is rounding noise of
-    the same size as the reference's own.
+    An element that misses the plain tolerance against the float32 oracle is therefore still
+    accepted if the KERNEL is within the same tolerance of the float64 evaluation -- the bound
+    the kernel can be held to whatever the oracle's own float32 noise is.  Such elements are
+    counted (HATCH) and the count is printed at the end of the test run.
     """
     got = np.asarray(got)
     want = np.asarray(want)
@@ -52,10 +55,13 @@ def assert_parity(got, want, what="", truth=None):
     scale = np.abs(want[fin]).max()
     tol = rtol * np.abs(want[fin]) + rtol * scale
     bad = np.abs(got[fin] - want[fin]) > tol
+    HATCH["elements_checked"] += int(fin.sum())
     if bad.any() and truth is not None:
         truth = np.asarray(truth)[fin]
-        oracle_noise = np.abs(want[fin].astype(truth.dtype) - truth).max()
-        bad &= np.abs(got[fin].astype(truth.dtype) - truth) > tol + 2 * oracle_noise
+        tscale = np.abs(truth).max()
+        ok_vs_truth = np.abs(got[fin].astype(truth.dtype) - truth) <= rtol * np.abs(truth) + rtol * tscale
+        HATCH["accepted_via_f64_truth"] += int((bad & ok_vs_truth).sum())
+        bad &= ~ok_vs_truth
     if bad.any():
         np.testing.assert_allclose(got[fin], want[fin], rtol=rtol, atol=rtol * scale, err_msg=what)
 
