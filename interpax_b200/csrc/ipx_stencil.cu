@@ -477,6 +477,35 @@ __device__ __forceinline__ void st_cp_async16(unsigned smem_dst, const void* gme
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void st_cp_async_wait() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+// ---- bulk asynchronous copies (the TMA unit's 1-D form) completing on an mbarrier ----
+__device__ __forceinline__ void st_mbar_init(unsigned mbar_s, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(mbar_s), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void st_mbar_expect_tx(unsigned mbar_s, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar_s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void st_mbar_wait(unsigned mbar_s, unsigned phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "IPX_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra IPX_MBAR_DONE;\n"
+      "bra IPX_MBAR_WAIT;\n"
+      "IPX_MBAR_DONE:\n"
+      "}\n" ::"r"(mbar_s), "r"(phase) : "memory");
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void st_bulk_g2s(unsigned smem_dst, const void* gmem_src, unsigned bytes, unsigned mbar_s) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_dst),
+               "l"(gmem_src), "r"(bytes), "r"(mbar_s)
+               : "memory");
+}
+#ifndef IPX_ST_BULK
+#define IPX_ST_BULK 1  // 1: table rows travel by cp.async.bulk (UBLKCP) + mbarrier; 0: by cp.async (LDGSTS)
+#endif
+
 __device__ __forceinline__ void st_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 // wait until at most N of the most recently committed groups are still in flight
 template <int N> __device__ __forceinline__ void st_cp_async_wait_group() {
@@ -545,7 +574,7 @@ template <typename T, int ND> struct StDenseCfg {
   static constexpr int ROW_BYTES = NR * kStWin * (int)sizeof(T);  // staged rows of one warp
   static constexpr int WX_BYTES = ND > 1 ? 16 * 32 * (int)sizeof(T) : 0;  // first-axis taps
   static constexpr int CQ_BYTES = ND * Q * (int)sizeof(T) * 32;   // next quad's coordinates
-  static constexpr int WARP_BYTES = ROW_BYTES + WX_BYTES + CQ_BYTES;
+  static constexpr int WARP_BYTES = ROW_BYTES + WX_BYTES + CQ_BYTES + 16;  // + the warp's mbarrier
 };
 
 template <typename T, int ND, int TAPS, bool DEVP, bool ORD0, int WM>
@@ -589,6 +618,11 @@ stencil_dense_kernel(const __grid_constant__ StArgs<T, ND> a) {
   constexpr int CPQ = Q * (int)sizeof(T) / 16;  // 16-byte chunks per quad and axis
   char* const cq = wbase + Cfg::ROW_BYTES + Cfg::WX_BYTES + lane * 16;
   const unsigned cq_s = (unsigned)__cvta_generic_to_shared(cq);
+  // the warp's mbarrier: completion of the bulk copies of one group pass
+  const unsigned mbar_s = rows_s + Cfg::ROW_BYTES + Cfg::WX_BYTES + Cfg::CQ_BYTES;
+  unsigned mbar_phase = 0;
+  if (IPX_ST_BULK && lane == 0) st_mbar_init(mbar_s, 1);
+  __syncwarp();
   auto stage_coords = [&](int64_t rn) {
     if (rn < 0) return;
     const int64_t q0 = rn * (32 * Q) + Q * lane;
@@ -723,6 +757,19 @@ stencil_dense_kernel(const __grid_constant__ StArgs<T, ND> a) {
       // (and not past the row's end)
       const int zhi = __reduce_max_sync(0xffffffffu, fit ? kmin : 0);
       const int nch = min((zhi - 1 - zs + TAPS + EPC - 1) / EPC, (pitch - zs) / EPC);
+#if IPX_ST_BULK
+      // one bulk copy per table row (the TMA unit moves the bytes; no per-lane address loop),
+      // all of them completing on the warp's mbarrier
+      if (lane == 0) st_mbar_expect_tx(mbar_s, (unsigned)(NR * nch * 16));
+      __syncwarp();
+      if (lane < NR) {
+        const int r = lane;
+        int64_t ro = 0;
+        if (ND == 3) ro = (int64_t)(r >> 2) * a.ax[0].stride + (int64_t)(r & 3) * a.ax[1].stride;
+        if (ND == 2) ro = (int64_t)r * a.ax[0].stride;
+        st_bulk_g2s(rows_s + r * (CH * 16), a.tab + co + ro + zs, (unsigned)(nch * 16), mbar_s);
+      }
+#else
       constexpr int LPR = 32 / NR;  // lanes per row
       const int r = lane / LPR, k0 = lane % LPR;
       int64_t ro = 0;
@@ -735,6 +782,7 @@ stencil_dense_kernel(const __grid_constant__ StArgs<T, ND> a) {
         src += LPR * EPC;
         dst += LPR * 16;
       }
+#endif
       st_cp_async_commit();
     };
     if (todo) begin_pass();
@@ -768,7 +816,12 @@ stencil_dense_kernel(const __grid_constant__ StArgs<T, ND> a) {
 #pragma unroll
     for (int s = 0; s < Q; ++s) acc[s] = T(0);
     while (todo) {
+#if IPX_ST_BULK
+      st_mbar_wait(mbar_s, mbar_phase);
+      mbar_phase ^= 1u;
+#else
       if (first_pass) st_cp_async_wait_group<1>(); else st_cp_async_wait();
+#endif
       first_pass = false;
       __syncwarp();
       if (fit) {
