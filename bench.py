@@ -480,15 +480,23 @@ def run_ours(args):
         sampler.active = False
         launches += int(lib.ipx_launch_count()) - l0
         dt_rank = dt
+        agg_gbs = 4 * nq * elem / dt_rank / 1e9
         if world > 1:
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
+            t = torch.tensor([agg_gbs], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            agg_gbs = float(t.item())
         barrier()
         e2e = {"value": world * nq / dt, "unit": "queries/s", "h2d_bytes_per_step": 3 * nq * elem,
                "d2h_bytes_per_step": nq * elem, "ms_per_step": dt * 1e3, "steps": e_steps,
                "query_order": "cell-sorted",
                "rank0_h2d_plus_d2h_gbs": 4 * nq * elem / dt_rank / 1e9,
+               "all_ranks_h2d_plus_d2h_gbs": agg_gbs,
+               "bound": "PCIe / host memory: every query moves 4 x %d bytes between pinned host memory and the "
+                        "GPU; one rank alone sustains about 67 GB/s (50 in + 17 out, full duplex), and the "
+                        "ranks of one node share the host's memory and PCIe root complexes" % elem,
                "host_binding": HOST_BINDING.get("note")}
         del hq, hout
 

@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import threading
 from typing import Any
 
 import numpy as np
@@ -195,14 +196,20 @@ def _slopes_dev(x: torch.Tensor, f: torch.Tensor, method: str, axis: int, kwargs
     opts.c = float(kwargs.get("c", 0)) if method == "cardinal" else 0.0
     keep = []
     if method == "cubic2":
-        bcs = _validate_bc(kwargs.get("bc_type", "not-a-knot"), f.shape[:axis] + f.shape[axis + 1:])
+        # (complex data arrives as a trailing (re, im) pair: the boundary values have the complex shape)
+        expect = f.shape[:axis] + f.shape[axis + 1:]
+        bcs = _validate_bc(kwargs.get("bc_type", "not-a-knot"), expect[:-1] if cplx else expect)
         kinds, vals = [], []
         for kind, val in bcs:
             kinds.append(kind)
             if val is None:
                 vals.append(None)
             else:
-                v = _to_dev(val, _T2NP[f.dtype], f.device).reshape(-1)
+                if cplx:
+                    cdt = np.complex128 if f.dtype == torch.float64 else np.complex64
+                    v = torch.view_as_real(_to_dev(val, cdt, f.device).contiguous()).reshape(-1)
+                else:
+                    v = _to_dev(val, _T2NP[f.dtype], f.device).reshape(-1)
                 keep.append(v)
                 vals.append(v.data_ptr())
         opts.bc_start, opts.bc_end = kinds
@@ -451,31 +458,60 @@ def _eval_stencil_dev(ndim, qs, knots, sknots, ns, halo, code, c, mask, params, 
 # chunks on a few CUDA streams, so the H2D copy of chunk c+1, the kernel of chunk c and the
 # D2H copy of chunk c-1 overlap (PCIe is full duplex).  Pinned buffers make the copies truly
 # asynchronous; pageable ones still work.
-_HOST_CHUNK = 1 << 22
+_HOST_CHUNK = 1 << 22            # queries per chunk at most
+_HOST_CHUNK_MIN = 1 << 16
+_HOST_OUT_BYTES = 256 << 20      # result staging per stream: the chunk shrinks for wide batches
 _HOST_STREAMS = 3
-_pipes: dict = {}
+_HOST_CACHE_BYTES = 2 << 30      # device memory the cached pipes may hold altogether
+_pipes: dict = {}                # (thread, device) -> _HostPipe
+_pipes_lock = threading.Lock()
 
 
-def launches_per_host_call(nq: int) -> int:
-    """Kernel launches one host-resident call of nq queries makes (for bench accounting)."""
-    return max(1, -(-int(nq) // _HOST_CHUNK))
+def _host_chunk(batch: int, elem: int) -> int:
+    """Queries per chunk: as many as fit _HOST_OUT_BYTES of results, within [2^16, 2^22]."""
+    return int(min(_HOST_CHUNK, max(_HOST_CHUNK_MIN, _HOST_OUT_BYTES // max(1, batch * elem))))
+
+
+def launches_per_host_call(nq: int, batch: int = 1, elem: int = 8) -> int:
+    """Chunks (evaluation calls) one host-resident call of nq queries makes."""
+    return max(1, -(-int(nq) // _host_chunk(batch, elem)))
 
 
 class _HostPipe:
-    def __init__(self, dev, tdt, ndim, batch):
+    """Streams + flat device staging buffers of one (thread, device); buffers are byte arrays
+    viewed per call, so one pipe serves every dtype, dimension and batch width."""
+
+    def __init__(self, dev):
+        self.dev = dev
         self.streams = [torch.cuda.Stream(device=dev) for _ in range(_HOST_STREAMS)]
-        self.q = [[torch.empty(_HOST_CHUNK, dtype=tdt, device=dev) for _ in range(ndim)]
-                  for _ in range(_HOST_STREAMS)]
-        self.out = [torch.empty(_HOST_CHUNK * batch, dtype=tdt, device=dev) for _ in range(_HOST_STREAMS)]
+        self.qbuf = [None] * _HOST_STREAMS
+        self.obuf = [None] * _HOST_STREAMS
+
+    def nbytes(self):
+        return sum(b.numel() for b in self.qbuf + self.obuf if b is not None)
+
+    def views(self, k, tdt, ndim, chunk, batch):
+        elem = torch.empty((), dtype=tdt).element_size()
+        need_q, need_o = ndim * chunk * elem, chunk * batch * elem
+        if self.qbuf[k] is None or self.qbuf[k].numel() < need_q:
+            self.qbuf[k] = torch.empty(need_q, dtype=torch.uint8, device=self.dev)
+        if self.obuf[k] is None or self.obuf[k].numel() < need_o:
+            self.obuf[k] = torch.empty(need_o, dtype=torch.uint8, device=self.dev)
+        q = self.qbuf[k][:need_q].view(tdt).view(ndim, chunk)
+        o = self.obuf[k][:need_o].view(tdt)
+        return q, o
 
 
-def _host_pipe(dev, tdt, ndim, batch) -> _HostPipe:
-    key = (dev.index, tdt, ndim, batch)
-    if key not in _pipes:
-        if len(_pipes) > 8:
-            _pipes.clear()
-        _pipes[key] = _HostPipe(dev, tdt, ndim, batch)
-    return _pipes[key]
+def _host_pipe(dev) -> _HostPipe:
+    key = (threading.get_ident(), dev.index)
+    with _pipes_lock:
+        pipe = _pipes.get(key)
+        if pipe is None:
+            # bound what the cache holds: drop other threads' / devices' pipes first
+            while _pipes and sum(p.nbytes() for p in _pipes.values()) > _HOST_CACHE_BYTES:
+                _pipes.pop(next(iter(_pipes)))
+            pipe = _pipes[key] = _HostPipe(dev)
+        return pipe
 
 
 def _run_host(dev, qd, batch, launch, out_host):
@@ -485,23 +521,29 @@ def _run_host(dev, qd, batch, launch, out_host):
     nq = qd[0].numel()
     if nq == 0:
         return
-    pipe = _host_pipe(dev, qd[0].dtype, ndim, batch)
+    pipe = _host_pipe(dev)
+    tdt = qd[0].dtype
+    chunk = _host_chunk(batch, qd[0].element_size())
     cur = torch.cuda.current_stream()
     for s in pipe.streams:
         s.wait_stream(cur)
-    for c, lo in enumerate(range(0, nq, _HOST_CHUNK)):
-        hi = min(nq, lo + _HOST_CHUNK)
+    for c, lo in enumerate(range(0, nq, chunk)):
+        hi = min(nq, lo + chunk)
         m = hi - lo
         k = c % _HOST_STREAMS
         with torch.cuda.stream(pipe.streams[k]):
-            dq = [pipe.q[k][ax][:m] for ax in range(ndim)]
+            qv, ov = pipe.views(k, tdt, ndim, chunk, batch)
+            dq = [qv[ax][:m] for ax in range(ndim)]
             for ax in range(ndim):
                 dq[ax].copy_(qd[ax][lo:hi], non_blocking=True)
-            dout = pipe.out[k][: m * batch].view(m, batch)
+            dout = ov[: m * batch].view(m, batch)
             launch(dq, dout)
             out_host[lo:hi].copy_(dout, non_blocking=True)
     for s in pipe.streams:
         s.synchronize()
+    if pipe.nbytes() > _HOST_CACHE_BYTES:  # an unusually wide call: do not keep its buffers
+        with _pipes_lock:
+            _pipes.pop((threading.get_ident(), dev.index), None)
 
 
 # --------------------------------------------------------------------------- front end
@@ -769,8 +811,10 @@ def approx_df(x, f, method="cubic", axis=-1, **kwargs):
     want_torch = isinstance(x, torch.Tensor) or isinstance(f, torch.Tensor)
     errorif(method not in _SLOPE_CODE, ValueError, f"got unknown method {method}")
     dev = _device()
-    fdt = _promote([f])
     xdt = _promote([x])
+    # dxi * df promotes with the knots (_fd_derivs.py:84-90): float32 data on float64 knots gives
+    # a float64 result, and the knots are never rounded down before they are differenced
+    fdt = np.dtype(np.result_type(_promote([f]), xdt))
     cplx = bool(np.issubdtype(fdt, np.complexfloating))
     rdt = np.dtype(np.float64) if fdt in (np.float64, np.complex128) else np.dtype(np.float32)
     ft = _to_dev(f, fdt, dev)

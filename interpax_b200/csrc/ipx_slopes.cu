@@ -171,12 +171,15 @@ __device__ __forceinline__ T akima_m(const SlopeArgs<T>& a, int64_t base, int j)
   return j == n + 1 ? mp1 : T(2) * mp1 - mn;
 }
 
+// max over non-negative values AND NaN: jnp.max (_fd_derivs.py:421) propagates a NaN, which makes
+// the threshold NaN and sends every node to the fall-back slope.  A NaN is stored as the positive
+// quiet NaN, whose bit pattern compares above every finite value and +inf.
 __device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
-  atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  atomicMax(reinterpret_cast<int*>(addr), v != v ? 0x7fc00000 : __float_as_int(v));
 }
 __device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
   atomicMax(reinterpret_cast<unsigned long long*>(addr),
-            (unsigned long long)__double_as_longlong(v));
+            v != v ? 0x7ff8000000000000ull : (unsigned long long)__double_as_longlong(v));
 }
 
 template <typename T> __global__ void akima_init_kernel(T* gmax) { *gmax = T(0); }
@@ -192,14 +195,14 @@ __global__ void akima_max_kernel(const SlopeArgs<T> a, T* __restrict__ gmax) {
     T m1 = akima_m(a, base, k), m2 = akima_m(a, base, k + 1);
     T m3 = akima_m(a, base, k + 2), m4 = akima_m(a, base, k + 3);
     T f12 = t_abs(m4 - m3) + t_abs(m2 - m1);
-    if (f12 > local) local = f12;
+    if (f12 > local || f12 != f12) local = f12;  // (a NaN sticks: nothing compares above it)
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
     T o = __shfl_xor_sync(0xffffffffu, local, off);
-    if (o > local) local = o;
+    if (o > local || o != o) local = o;
   }
-  if ((threadIdx.x & 31) == 0 && local > T(0)) atomic_max_nonneg(gmax, local);
+  if ((threadIdx.x & 31) == 0 && (local > T(0) || local != local)) atomic_max_nonneg(gmax, local);
 }
 
 template <typename T>
@@ -265,14 +268,14 @@ __global__ void akima_max_complex_kernel(const SlopeArgs<T> a, T* __restrict__ g
     AkimaPair<T> p;
     akima_pair(a, base, k, p);
     T f12 = p.w43 + p.w21;
-    if (f12 > local) local = f12;
+    if (f12 > local || f12 != f12) local = f12;  // (a NaN sticks: nothing compares above it)
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
     T o = __shfl_xor_sync(0xffffffffu, local, off);
-    if (o > local) local = o;
+    if (o > local || o != o) local = o;
   }
-  if ((threadIdx.x & 31) == 0 && local > T(0)) atomic_max_nonneg(gmax, local);
+  if ((threadIdx.x & 31) == 0 && (local > T(0) || local != local)) atomic_max_nonneg(gmax, local);
 }
 
 template <typename T>

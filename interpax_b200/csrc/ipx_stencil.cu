@@ -1225,7 +1225,9 @@ static int launch_stencil(const T* const* q, int64_t nq, const T* const* knots, 
   // 256^3 f64 -- so the automatic choice uses it in 1-D / 2-D only; the hint still selects it)
   const bool dense = dense_ok && ND < 3 && (double)nq >= 3.0 * cells;
   const bool rec_random = records != nullptr && (ND == 2 || (ND == 3 && halo_bytes > kL2TableBytes));
-  const bool rec_quads = records != nullptr && ND == 3 && dense_ok && (double)nq >= 3.0 * cells;
+  // (the tile kernel on the records overtakes the sparse shape between three and six queries per
+  // cell: 256^3 f64, 5e7 queries 1.73 vs 1.44 ms, 1e8 queries 1.86 vs 2.83 ms)
+  const bool rec_quads = records != nullptr && ND == 3 && dense_ok && (double)nq >= 4.0 * cells;
   if (!dense && !rec_random && !rec_quads) return st_launch_q<T, ND, false, 4>(a, d, s);  // one candidate: no probe
   stencil_probe_kernel<T, ND, IPX_STENCIL_TAPS><<<1, 256, 0, s>>>(a, workspace);
   count_launches(1);
