@@ -347,6 +347,38 @@ int ipx_vjp_tables_f64(int32_t ndim, const double* const* q, int64_t nq, const d
                        void* stream);
 
 /* ---------------------------------------------------------------------------------
+ * Derivatives of the cubic evaluation with respect to the KNOTS and to f, for the three-point
+ * stencils (IPX_SLOPE_CUBIC, IPX_SLOPE_CARDINAL): the map (knots, f) -> interpNd(q, knots, f) with
+ * the slope chain inside, which is what the reference's AD tests differentiate
+ * (tests/test_interpolate.py:542-637: jacfwd / jacrev with respect to the knot vector; JAX derives
+ * it by tracing interpax/_spline.py:1027-1099 and _fd_derivs.py:79-101, 303-324).
+ * Arguments as for ipx_eval_stencil_* except that `f` is the ORIGINAL table (C order, extents n,
+ * scalar-valued), perm is a HOST array of ndim device pointers or NULL (IPX_PERIODIC axes need
+ * knots sorted inside one period, perm NULL), and:
+ *   ipx_vjp_stencil_*  reverse mode: grad_knots[ax][k] += sum_q cotangent[q] d out[q]/d x_ax[k]
+ *                      (HOST array of ndim device pointers, n[ax] entries each, entries may be NULL),
+ *                      grad_f += the same with respect to f (or NULL).  ACCUMULATES: zero first.
+ *   ipx_jvp_stencil_*  forward mode: tangent[q] = sum_k knots_dot[ax][k] d out[q]/d x_ax[k]
+ *                      + sum f_dot * d out[q]/d f   (either may be NULL = zero tangent).
+ * Gradients are with respect to the caller's knot vectors (on periodic axes: the n original
+ * knots).  Queries replaced by an extrapolation fill have zero derivative.  Other slope
+ * methods: IPX_EUNSUPPORTED.
+ * --------------------------------------------------------------------------------- */
+#define IPX_DECL_GRAD(SUF, T)                                                                             \
+  int ipx_vjp_stencil_##SUF(int32_t ndim, const T* const* q, int64_t nq, const T* const* knots,           \
+                            const T* const* slope_knots, const int32_t* const* perm, const int32_t* n,    \
+                            const T* f, int32_t slope_method, double c, int32_t periodic_mask,            \
+                            const ipx_params* params, int32_t params_on_device, const T* cotangent,       \
+                            T* const* grad_knots, T* grad_f, void* stream);                               \
+  int ipx_jvp_stencil_##SUF(int32_t ndim, const T* const* q, int64_t nq, const T* const* knots,           \
+                            const T* const* slope_knots, const int32_t* const* perm, const int32_t* n,    \
+                            const T* f, int32_t slope_method, double c, int32_t periodic_mask,            \
+                            const ipx_params* params, int32_t params_on_device,                           \
+                            const T* const* knots_dot, const T* f_dot, T* tangent, void* stream);
+IPX_DECL_GRAD(f32, float)
+IPX_DECL_GRAD(f64, double)
+
+/* ---------------------------------------------------------------------------------
  * Piecewise polynomials in the power basis (interpax/_ppoly.py).  Coefficients as the
  * reference holds them after its moveaxis: c[(j*m + i)*batch + b] multiplies
  * (x - x[i])^(k-1-j) on piece i, for trailing element b; x has m+1 breakpoints.

@@ -19,6 +19,8 @@ from .api import (
     interp1d,
     interp2d,
     interp3d,
+    jvp_knots,
+    vjp_knots,
     vjp_tables,
 )
 from .ppoly import Akima1DInterpolator, CubicHermiteSpline, CubicSpline, PchipInterpolator, PPoly
@@ -37,6 +39,8 @@ __all__ = [
     "interp1d",
     "interp2d",
     "interp3d",
+    "jvp_knots",
+    "vjp_knots",
     "vjp_tables",
 ]
 

@@ -69,7 +69,7 @@ SYMBOLS = (
     + [
         f"ipx_{name}_{t}"
         for name in ("bin_index", "slopes", "slopes_pack", "periodic_knots", "pad_periodic", "pack", "cell_order", "cell_sort", "gather", "halo_table", "eval_stencil",
-                     "gather_multi", "scatter", "vjp_tables", "ppoly_eval", "ppoly_pack", "ppoly_from_hermite",
+                     "gather_multi", "scatter", "vjp_tables", "vjp_stencil", "jvp_stencil", "ppoly_eval", "ppoly_pack", "ppoly_from_hermite",
                      "ppoly_derivative", "ppoly_antiderivative")
         for t in ("f32", "f64")
     ]
@@ -168,6 +168,14 @@ def _declare(lib: C.CDLL) -> None:
         f.restype = C.c_int
         f.argtypes = [i32, C.POINTER(vp), i64, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), i64, i32, i32,
                       C.POINTER(Params), i32, vp, C.POINTER(vp), vp]
+        f = getattr(lib, f"ipx_vjp_stencil_{t}")
+        f.restype = C.c_int
+        f.argtypes = [i32, C.POINTER(vp), i64, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), vp, i32,
+                      C.c_double, i32, C.POINTER(Params), i32, vp, C.POINTER(vp), vp, vp]
+        f = getattr(lib, f"ipx_jvp_stencil_{t}")
+        f.restype = C.c_int
+        f.argtypes = [i32, C.POINTER(vp), i64, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), vp, i32,
+                      C.c_double, i32, C.POINTER(Params), i32, C.POINTER(vp), vp, vp, vp]
         f = getattr(lib, f"ipx_gather_multi_{t}")
         f.restype = C.c_int
         f.argtypes = [i32, C.POINTER(vp), vp, i64, C.POINTER(vp), vp]

@@ -877,6 +877,84 @@ def vjp_tables(qs, knots, fshape, cotangent, method="cubic", derivative=0, extra
     return out if io.want_torch else {k: v.cpu().numpy() for k, v in out.items()}
 
 
+def _grad_stencil_setup(qs, knots, f, method, derivative, extrap, period, functional, kwargs, dtype_item):
+    ndim = len(knots)
+    errorif(ndim not in (1, 2, 3) or len(qs) != ndim, ValueError, "need 1, 2 or 3 query and knot arrays")
+    errorif(method not in _STENCIL_METHODS, NotImplementedError,
+            "knot / f derivatives are available for method = cubic, cardinal, catmull-rom "
+            "(local linear stencils); cubic2, monotonic and akima are not covered")
+    fshape = _shape(f)
+    _check_shapes(ndim, knots, fshape)
+    errorif(len(fshape) != ndim, NotImplementedError, "scalar-valued f only")
+    io = _Inputs(qs, knots, dtype_item)
+    errorif(io.complex, NotImplementedError, "real data only")
+    kn = [io.coords(k) for k in knots]
+    qd, qshape, _ = io.queries(qs)
+    qd = [q.to(io.dev) for q in qd]
+    ft = io.table(f)
+    periods = _parse_ndarg(period, ndim)
+    params = _make_params(ndim, _parse_ndarg(derivative, ndim), _parse_extrap(extrap, ndim), periods)
+    mask, kuse, perms = 0, list(kn), [None] * ndim
+    for ax in range(ndim):
+        if periods[ax] is None:
+            continue
+        xpad, perm = _periodic_knots_dev(kn[ax], periods[ax])
+        kuse[ax] = xpad
+        if functional:
+            mask |= L.IPX_PAD_FIRST(ax)
+            perms[ax] = perm
+        else:
+            ident = torch.arange(perm.numel(), dtype=perm.dtype, device=perm.device)
+            errorif(not bool(torch.equal(perm, ident)), NotImplementedError,
+                    "class-form periodic axes need knots sorted inside one period")
+            mask |= L.IPX_PERIODIC(ax)
+    code = _STENCIL_METHODS[method]
+    c = float(kwargs.get("c", 0)) if method == "cardinal" else 0.0
+    narr = (C.c_int32 * ndim)(*[int(fshape[ax]) for ax in range(ndim)])
+    return io, ndim, qd, qshape, kn, kuse, perms, ft, params, mask, code, c, narr
+
+
+def vjp_knots(qs, knots, f, cotangent, method="cubic", derivative=0, extrap=False, period=None,
+              functional=True, **kwargs):
+    """Reverse-mode rule of ``interp{1,2,3}d(q, knots, f, method)`` / ``Interpolator{1,2,3}D(knots, f,
+    method)(q)`` with respect to the KNOTS and to ``f``, slope chain included -- what
+    ``jax.jacrev(lambda xp: interp1d(x, xp, fp, method))`` computes in the reference
+    (tests/test_interpolate.py:542-637).  ``cotangent`` has the shape of the output.  Returns
+    ``{"x": ..., ["y", "z",] "f": ...}``.  ``functional``: which of the reference's two periodic
+    conventions (slopes on the padded knots, or -- the classes -- on the original ones).
+    method = cubic, cardinal, catmull-rom."""
+    io, ndim, qd, qshape, kn, kuse, perms, ft, params, mask, code, c, narr = _grad_stencil_setup(
+        qs, knots, f, method, derivative, extrap, period, functional, kwargs, cotangent)
+    cot = _to_dev(cotangent, io.rdt, io.dev).reshape(-1)
+    errorif(cot.numel() != qd[0].numel(), ValueError, "cotangent must have the shape of the output")
+    gk = [torch.zeros_like(k) for k in kn]
+    gf = torch.zeros_like(ft)
+    fn = getattr(L.load(), f"ipx_vjp_stencil_{_suffix(ft)}")
+    L.check(fn(ndim, _ptr_array(qd), qd[0].numel(), _ptr_array(kuse), _ptr_array(kn), _ptr_array(perms), narr,
+               _ptr(ft), code, c, mask, C.byref(params), 0, _ptr(cot), _ptr_array(gk), _ptr(gf), _stream()),
+            "ipx_vjp_stencil")
+    out = dict(zip("xyz", gk))
+    out["f"] = gf
+    return out if io.want_torch else {k: v.cpu().numpy() for k, v in out.items()}
+
+
+def jvp_knots(qs, knots, f, knots_dot, f_dot=None, method="cubic", derivative=0, extrap=False, period=None,
+              functional=True, **kwargs):
+    """Forward-mode rule of the same map: the tangent of the output for tangents ``knots_dot``
+    (a tuple, entries may be None) and ``f_dot`` (or None)."""
+    io, ndim, qd, qshape, kn, kuse, perms, ft, params, mask, code, c, narr = _grad_stencil_setup(
+        qs, knots, f, method, derivative, extrap, period, functional, kwargs, f)
+    kd = [None if v is None else _to_dev(v, io.rdt, io.dev).reshape(-1) for v in knots_dot]
+    fd = None if f_dot is None else _to_dev(f_dot, io.rdt, io.dev).contiguous()
+    tan = torch.empty(qd[0].numel(), dtype=io.tdt, device=io.dev)
+    fn = getattr(L.load(), f"ipx_jvp_stencil_{_suffix(ft)}")
+    L.check(fn(ndim, _ptr_array(qd), qd[0].numel(), _ptr_array(kuse), _ptr_array(kn), _ptr_array(perms), narr,
+               _ptr(ft), code, c, mask, C.byref(params), 0, _ptr_array(kd), _ptr(fd), _ptr(tan), _stream()),
+            "ipx_jvp_stencil")
+    tan = tan.reshape(qshape)
+    return tan if io.want_torch else tan.cpu().numpy()
+
+
 def bin_index(x, q):
     """``clip(searchsorted(x, q, side="right"), 1, len(x)-1)`` on the device -- the interval
     lookup of _spline.py:571 on its own (int32)."""

@@ -1,0 +1,156 @@
+"""Derivatives with respect to the knots and to f, modelled on the
+reference's TestAD (tests/test_interpolate.py:542-637): there jax.jacfwd and jax.jacrev of
+interpNd / InterpolatorND with respect to the knot vector must agree with each other and with
+finite differences.  Here: ipx.jvp_knots (forward) against ipx.vjp_knots (reverse) through
+the dot-product identity, both against central finite differences of the ORACLE (and of the
+kernels' own forward evaluation), on the reference's test setups and on harder ones
+(non-uniform knots, periodic axes in both conventions, derivative orders, extrapolation)."""
+
+import numpy as np
+import pytest
+
+import interpax_b200 as ipx
+from oracle import interpax_np as O
+
+pytestmark = pytest.mark.gpu
+
+OFUN = (O.interp1d, O.interp2d, O.interp3d)
+OCLS = (O.Interpolator1D, O.Interpolator2D, O.Interpolator3D)
+
+
+def fd_knots(fun, knots, ax, h=1e-6):
+    """Central finite differences d out / d knots[ax][k] -> (nq, n)."""
+    cols = []
+    for k in range(len(knots[ax])):
+        kp = [v.copy() for v in knots]
+        km = [v.copy() for v in knots]
+        kp[ax][k] += h
+        km[ax][k] -= h
+        cols.append((fun(kp) - fun(km)) / (2 * h))
+    return np.stack(cols, axis=-1)
+
+
+def jacobians(qs, knots, f, method, functional, **kw):
+    """(reverse, forward) Jacobians d out[q] / d knots[ax][k] from the kernels, per axis."""
+    ndim = len(knots)
+    nq = len(qs[0])
+    rev = [np.zeros((nq, len(k))) for k in knots]
+    for q in range(nq):
+        cot = np.zeros(nq)
+        cot[q] = 1.0
+        g = ipx.vjp_knots(qs, knots, f, cot, method, functional=functional, **kw)
+        for ax in range(ndim):
+            rev[ax][q] = g["xyz"[ax]]
+    fwd = [np.zeros((nq, len(k))) for k in knots]
+    for ax in range(ndim):
+        for k in range(len(knots[ax])):
+            dots = [None] * ndim
+            dots[ax] = np.zeros(len(knots[ax]))
+            dots[ax][k] = 1.0
+            fwd[ax][:, k] = ipx.jvp_knots(qs, knots, f, tuple(dots), None, method, functional=functional, **kw)
+    return rev, fwd
+
+
+@pytest.mark.parametrize("method", ["cubic", "cardinal", "catmull-rom"])
+def test_reference_test_ad_interp1d(method):
+    """tests/test_interpolate.py:543-569 for the methods with a local linear stencil."""
+    xp = np.linspace(0, 2 * np.pi, 10)
+    x = np.linspace(0, 2 * np.pi, 20)
+    fp = np.sin(xp)
+    kw = {"c": 0.3} if method == "cardinal" else {}
+    for functional in (True, False):
+        rev, fwd = jacobians((x,), (xp,), fp, method, functional, **kw)
+        np.testing.assert_allclose(fwd[0], rev[0], rtol=1e-13, atol=1e-13)  # jacfwd == jacrev
+        ofun = (lambda k: O.interp1d(x, k[0], fp, method, **kw)) if functional else (
+            lambda k: O.Interpolator1D(k[0], fp, method, **kw)(x))
+        jd = fd_knots(ofun, (xp,), 0)
+        # (finite differences give nan at the end points, as the reference's test notes)
+        np.testing.assert_allclose(fwd[0][1:-1], jd[1:-1], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("method", ["cubic", "cardinal"])
+def test_reference_test_ad_interp2d_3d(method):
+    """tests/test_interpolate.py:571-637: the Jacobian with respect to the first knot vector."""
+    kw = {"c": 0.0} if method == "cardinal" else {}
+    xp, yp = np.linspace(0, 4 * np.pi, 20), np.linspace(0, 2 * np.pi, 20)
+    x = y = np.linspace(0, 2 * np.pi, 30)
+    xxp, yyp = np.meshgrid(xp, yp, indexing="ij")
+    fp = np.sin(xxp) * np.cos(yyp)
+    rev, fwd = jacobians((x, y), (xp, yp), fp, method, True, **kw)
+    np.testing.assert_allclose(fwd[0], rev[0], rtol=1e-13, atol=1e-13)
+    jd = fd_knots(lambda k: O.interp2d(x, y, k[0], k[1], fp, method, **kw), (xp, yp), 0)
+    np.testing.assert_allclose(fwd[0][1:-1], jd[1:-1], rtol=1e-6, atol=1e-6)
+    xp, yp, zp = np.linspace(0, np.pi, 10), np.linspace(0, 2 * np.pi, 15), np.linspace(0, 1, 12)
+    x, y, z = np.linspace(0, np.pi, 13), np.linspace(0, 2 * np.pi, 13), np.linspace(0, 1, 13)
+    xxp, yyp, zzp = np.meshgrid(xp, yp, zp, indexing="ij")
+    fp = np.sin(xxp) * np.cos(yyp) * zzp**2
+    for functional in (True, False):
+        rev, fwd = jacobians((x, y, z), (xp, yp, zp), fp, method, functional, **kw)
+        for ax in range(3):
+            np.testing.assert_allclose(fwd[ax], rev[ax], rtol=1e-12, atol=1e-12)
+        ofun = (lambda k: O.interp3d(x, y, z, *k, fp, method, **kw)) if functional else (
+            lambda k: O.Interpolator3D(*k, fp, method, **kw)(x, y, z))
+        for ax in range(3):
+            jd = fd_knots(ofun, (xp, yp, zp), ax)
+            np.testing.assert_allclose(fwd[ax][1:-1], jd[1:-1], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("ndim", [1, 2, 3])
+def test_knot_and_table_derivatives_general(ndim):
+    """Non-uniform knots, periodic axes in both of the reference's conventions, derivative
+    orders, extrapolation with fills: the reverse rule is the transpose of the forward rule
+    (random cotangent / tangents), and both match central differences of the oracle with
+    respect to every knot vector and to f."""
+    rng = np.random.default_rng(300 + ndim)
+    ns = [9, 7, 8][:ndim]
+    nq = 300
+    for trial in range(6):
+        functional = trial % 2 == 0
+        method = ["cubic", "cardinal", "catmull-rom"][trial % 3]
+        kw = {"c": 0.25} if method == "cardinal" else {}
+        knots = [np.sort(rng.uniform(0.05, 2.0, n)) for n in ns]
+        for k in knots:
+            k[0] = 0.05
+        f = rng.normal(size=ns)
+        per_axes = [bool((trial >> 1) & 1) and ax != ndim - 1 for ax in range(ndim)] if ndim > 1 else [trial >= 4]
+        period = tuple(2.3 if p else None for p in per_axes)
+        period = period[0] if ndim == 1 else period
+        deriv = tuple(int(v) for v in rng.integers(0, 3, ndim)) if trial % 3 == 1 else (0,) * ndim
+        dfun = deriv[0] if ndim == 1 else deriv
+        extrap = [True, (True, 0.5), False][trial % 3]
+        # queries away from the knots (the map is only piecewise smooth in the knots there)
+        qs = [rng.uniform(-0.3, 2.4, nq) for _ in range(ndim)]
+        what = f"nd={ndim} {method} functional={functional} per={period} d={deriv} ex={extrap}"
+        if functional:
+            ofun = lambda k, ff=f: OFUN[ndim - 1](*qs, *k, ff, method, dfun, extrap, period, **kw)
+        else:
+            ofun = lambda k, ff=f: OCLS[ndim - 1](*k, ff, method, extrap, period, **kw)(*qs, *deriv)
+        base = ofun(knots)
+        ok = np.isfinite(base)
+        cot = rng.normal(size=nq)
+        g = ipx.vjp_knots(qs, knots, f, cot, method, dfun, extrap, period, functional=functional, **kw)
+        kd = [rng.normal(size=n) for n in ns]
+        fd = rng.normal(size=ns)
+        tan = ipx.jvp_knots(qs, knots, f, tuple(kd), fd, method, dfun, extrap, period, functional=functional, **kw)
+        # transpose identity: <cot, J v> == <J^T cot, v>
+        lhs = float(np.dot(cot[ok], tan[ok]))
+        rhs = sum(float(np.dot(g["xyz"[ax]], kd[ax])) for ax in range(ndim)) + float(np.sum(g["f"] * fd))
+        assert np.all(tan[~ok] == 0)
+        assert abs(lhs - rhs) <= 1e-10 * max(1.0, abs(lhs)), what
+        # directional finite difference of the oracle along (kd, fd)
+        h = 1e-6
+        kp = [k + h * d for k, d in zip(knots, kd)]
+        km = [k - h * d for k, d in zip(knots, kd)]
+        num = (ofun(kp, f + h * fd) - ofun(km, f - h * fd)) / (2 * h)
+        smooth = ok & np.isfinite(num)
+        # drop queries whose cell changes under the perturbation (a knot crosses the query)
+        for ax in range(ndim):
+            P = period if ndim == 1 else period[ax]
+            for kk in (kp, km, knots):
+                kv, qv = (np.sort(np.mod(kk[ax], P)), np.mod(qs[ax], P)) if P is not None else (kk[ax], qs[ax])
+                cell = np.searchsorted(kv, qv, side="right")
+                if kk is kp:
+                    ref_cell = cell
+                smooth &= cell == ref_cell
+        scale = np.abs(num[smooth]).max()
+        np.testing.assert_allclose(tan[smooth], num[smooth], rtol=2e-5, atol=2e-6 * scale, err_msg=what)
