@@ -75,16 +75,35 @@ def errorif(cond, err=ValueError, msg=""):
         raise err(msg)
 
 
+_have_cuda = None
+_devices: dict = {}
+
+
 def _device() -> torch.device:
-    if not torch.cuda.is_available():
+    global _have_cuda
+    if _have_cuda is None:
+        _have_cuda = bool(torch.cuda.is_available())
+    if not _have_cuda:
         raise RuntimeError(
             "interpax_b200 needs a CUDA device: the query path is hand-written CUDA behind "
             "libipx.so and has no CPU fallback"
         )
-    return torch.device("cuda", torch.cuda.current_device())
+    idx = torch.cuda.current_device()
+    dev = _devices.get(idx)
+    if dev is None:
+        dev = _devices[idx] = torch.device("cuda", idx)
+    return dev
+
+
+try:  # the raw handle of the current stream without building a torch.cuda.Stream object per call
+    _raw_stream = torch._C._cuda_getCurrentRawStream
+except AttributeError:  # pragma: no cover
+    _raw_stream = None
 
 
 def _stream() -> int:
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -442,7 +461,8 @@ def _eval_stencil_dev(ndim, qs, knots, sknots, ns, halo, code, c, mask, params, 
     if out is None:
         out = torch.empty((nq, 1), dtype=dt, device=dev)
     idx = torch.empty((ndim, nq), dtype=torch.int32, device=dev) if return_index else None
-    ws = torch.empty(4, dtype=torch.int32, device=dev) if stencil_hint == L.IPX_STENCIL_AUTO else None
+    # (the device-side choice of kernel is made from 2^16 queries up: smaller calls need no scratch)
+    ws = torch.empty(4, dtype=torch.int32, device=dev) if stencil_hint == L.IPX_STENCIL_AUTO and nq >= (1 << 16) else None
     fn = getattr(lib, f"ipx_eval_stencil_{_suffix(qs[0])}")
     narr = (C.c_int32 * ndim)(*[int(n) for n in ns])
     rc = fn(ndim, _ptr_array(qs), nq, _ptr_array(knots), _ptr_array(sknots), narr, _ptr(halo), _ptr(records), code,
@@ -552,9 +572,17 @@ class _Inputs:
     (_spline.py:503-521, 663-689, 882-910)."""
 
     def __init__(self, qs, knots, f_dtype_item, stored=None):
+        self.dev = _device()
+        if stored is not None and all(isinstance(q, torch.Tensor) and q.dtype == stored.tdt for q in qs):
+            # queries already in the stored tables' type: nothing to promote (the common call of
+            # Interpolator*.__call__ with device tensors; saves the NumPy dtype algebra per call)
+            self.want_torch = True
+            self.xdt, self.fdt, self.rdt, self.tdt = stored.xdt, stored.fdt, stored.rdt, stored.tdt
+            self.complex = stored.complex
+            if np.result_type(stored.xdt, stored.rdt) == stored.xdt:
+                return
         self.want_torch = any(isinstance(a, torch.Tensor) for a in (*qs, *knots)) or (
             stored.want_torch if stored is not None else isinstance(f_dtype_item, torch.Tensor))
-        self.dev = _device()
         self.xdt = _promote([*knots, *qs])
         errorif(np.issubdtype(self.xdt, np.complexfloating), TypeError, "knots and queries must be real")
         fdt = stored.fdt if stored is not None else _promote([f_dtype_item])

@@ -620,16 +620,39 @@ template <typename T, int ND> static size_t tile_knot_bytes(const EvalArgs<T, ND
 
 // warps of one CTA: as many as the register file holds, fewer if the shared memory left beside
 // the knots does not hold that many per-warp tiles
-template <typename T, int ND, int RC, int QPL> static int tile_warps(const EvalArgs<T, ND>& a) {
-  static std::atomic<int> optin{0};  // opt-in shared memory per block of the current device
-  int lim = optin.load(std::memory_order_relaxed);
-  if (lim == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || lim <= 0)
-      lim = 48 * 1024;
-    optin.store(lim, std::memory_order_relaxed);
+// per-device launch constants, looked up once per device (immutable afterwards)
+struct TileDevice {
+  int dev, sms, smem_optin;
+};
+static TileDevice tile_device() {
+  constexpr int kMaxDev = 64;
+  static std::atomic<int> ready[kMaxDev];
+  static int sms[kMaxDev], optin[kMaxDev];
+  TileDevice d{0, 148, 48 * 1024};
+  cudaGetDevice(&d.dev);
+  if (d.dev < 0 || d.dev >= kMaxDev) return d;
+  if (ready[d.dev].load(std::memory_order_acquire) == 0) {
+    int s = 148, o = 48 * 1024;
+    if (cudaDeviceGetAttribute(&s, cudaDevAttrMultiProcessorCount, d.dev) != cudaSuccess) s = 148;
+    if (cudaDeviceGetAttribute(&o, cudaDevAttrMaxSharedMemoryPerBlockOptin, d.dev) != cudaSuccess || o <= 0)
+      o = 48 * 1024;
+    sms[d.dev] = s;
+    optin[d.dev] = o;
+    ready[d.dev].store(1, std::memory_order_release);
   }
+  d.sms = sms[d.dev];
+  d.smem_optin = optin[d.dev];
+  return d;
+}
+// experiment switches, read once per process (profiles/sweep_tile_modes.sh)
+static const char* tile_env(int which) {
+  static const char* const mode = getenv("IPX_TILE_MODE");
+  static const char* const runtime_flags = getenv("IPX_TILE_RUNTIME_FLAGS");
+  return which == 0 ? mode : runtime_flags;
+}
+
+template <typename T, int ND, int RC, int QPL> static int tile_warps(const EvalArgs<T, ND>& a) {
+  const int lim = tile_device().smem_optin;
   const long long room = (long long)lim - 1024 - (long long)tile_knot_bytes<T, ND>(a);  // 1 KB: static
   const long long fit = room / TileCfg<T, ND, RC, QPL>::WARP_TILE_BYTES;
   const int maxw = tile_max_threads<T>() / 32;
@@ -653,11 +676,21 @@ static bool launch_tile_wm(const EvalArgs<T, ND>& a, cudaStream_t s) {
                 : (ord0 ? eval_tile_kernel<T, ND, false, true, RC, TWO, -1>
                         : eval_tile_kernel<T, ND, false, false, RC, TWO, -1>);
   }
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-    return false;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // the opt-in shared-memory size of a kernel is a per-device attribute: raise it when a launch
+  // needs more than any earlier one on that device (never lowered), not on every launch
+  const TileDevice td = tile_device();
+  {
+    constexpr int kMaxDev = 64;
+    static std::atomic<int> granted[3][kMaxDev];  // per kernel variant of this instantiation
+    const int variant = WM >= 0 ? (ord0 ? 1 : 0) : (a.dp ? 2 : (ord0 ? 1 : 0));
+    const int slot = td.dev >= 0 && td.dev < kMaxDev ? td.dev : 0;
+    if ((int)smem > granted[variant][slot].load(std::memory_order_relaxed) || td.dev != slot) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return false;
+      granted[variant][slot].store((int)smem, std::memory_order_relaxed);
+    }
+  }
+  const int sms = td.sms;
   const int threads = warps * 32;
   int64_t need = (a.nq + QPL * threads - 1) / (QPL * threads);
   int64_t grid = sms;  // persistent: one CTA per SM
@@ -672,7 +705,7 @@ static bool launch_tile_wm(const EvalArgs<T, ND>& a, cudaStream_t s) {
 template <typename T, int ND, int RC, bool TWO = true>
 static bool launch_tile_rc(const EvalArgs<T, ND>& a, cudaStream_t s) {
   int mask = 0, pmask = 0;
-  bool ct = a.dp == nullptr && getenv("IPX_TILE_RUNTIME_FLAGS") == nullptr;
+  bool ct = a.dp == nullptr && tile_env(1) == nullptr;
   for (int ax = 0; ax < ND; ++ax) {
     const AxisDesc<T>& A = a.ax[ax];
     ct = ct && A.perm == nullptr;
@@ -729,7 +762,7 @@ static bool launch_tile(const EvalArgs<T, ND>& a, cudaStream_t s) {
         (double)a.nq < 5.0 * cells &&
         (two ? tile_warps<T, ND, 32, 2>(a) >= tile_warps<T, ND, 16, 2>(a)
              : tile_warps<T, ND, 32, 1>(a) >= tile_warps<T, ND, 16, 1>(a));
-    const char* e = getenv("IPX_TILE_MODE");  // experiment switch (profiles/sweep_tile_modes.sh)
+    const char* e = tile_env(0);  // experiment switch (profiles/sweep_tile_modes.sh)
     if (e != nullptr) {
       if (e[0] == 'a') return launch_tile_rc<T, ND, 16, true>(a, s);
       if (e[0] == 'b') return launch_tile_rc<T, ND, 16, false>(a, s);

@@ -42,8 +42,11 @@
 //          one-query path, so results never depend on the neighbours in the stream.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
+#include <unordered_map>
 
 #include "ipx_device.cuh"
 #include "ipx_halo.cuh"
@@ -1013,15 +1016,45 @@ __global__ void halo_kernel(const T* __restrict__ f, const HaloArgs<ND> h, int64
 // host side
 // ------------------------------------------------------------------------------------
 struct StDevice {
+  int dev;
   int sms;
   int smem_optin;
 };
 
+// per-device constants, looked up once per device (immutable afterwards)
 static bool st_device(StDevice& d) {
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return false;
-  if (cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
-  if (cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return false;
+  constexpr int kMaxDev = 64;
+  static std::atomic<int> ready[kMaxDev];
+  static int sms[kMaxDev], optin[kMaxDev];
+  if (cudaGetDevice(&d.dev) != cudaSuccess) return false;
+  if (d.dev < 0 || d.dev >= kMaxDev) {
+    return cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, d.dev) == cudaSuccess &&
+           cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d.dev) == cudaSuccess;
+  }
+  if (ready[d.dev].load(std::memory_order_acquire) == 0) {
+    int s_ = 0, o_ = 0;
+    if (cudaDeviceGetAttribute(&s_, cudaDevAttrMultiProcessorCount, d.dev) != cudaSuccess) return false;
+    if (cudaDeviceGetAttribute(&o_, cudaDevAttrMaxSharedMemoryPerBlockOptin, d.dev) != cudaSuccess) return false;
+    sms[d.dev] = s_;
+    optin[d.dev] = o_;
+    ready[d.dev].store(1, std::memory_order_release);
+  }
+  d.sms = sms[d.dev];
+  d.smem_optin = optin[d.dev];
+  return true;
+}
+
+// The opt-in shared-memory size of a kernel is a per-(kernel, device) attribute: raise it when a
+// launch needs more than any earlier one (never lowered), not on every launch.
+static bool st_grant_smem(const void* kern, int dev, size_t smem) {
+  static std::mutex mu;
+  static std::unordered_map<unsigned long long, size_t> granted;
+  const unsigned long long key = (unsigned long long)(uintptr_t)kern * 64ull + (unsigned long long)(dev & 63);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = granted.find(key);
+  if (it != granted.end() && it->second >= smem) return true;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+  granted[key] = smem;
   return true;
 }
 
@@ -1065,9 +1098,8 @@ static int st_launch_q(const StArgs<T, ND>& a, const StDevice& d, cudaStream_t s
     kern = a.dp ? stencil_sparse_kernel<T, ND, true, false>
                 : (ord0 ? stencil_sparse_kernel<T, ND, false, true> : stencil_sparse_kernel<T, ND, false, false>);
   }
-  if (smem > 32 * 1024 &&  // (static shared memory counts towards the 48 KB default limit too)
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-    return IPX_ELAUNCH;
+  // (static shared memory counts towards the 48 KB default limit too)
+  if (smem > 32 * 1024 && !st_grant_smem(reinterpret_cast<const void*>(kern), d.dev, smem)) return IPX_ELAUNCH;
   const int qpt = DENSE ? 4 : 1;
   int64_t need = (a.nq + (int64_t)threads * qpt - 1) / ((int64_t)threads * qpt);
   int64_t grid = d.sms;  // persistent: one CTA per SM
