@@ -31,6 +31,10 @@ def header_symbols():
     for d in (1, 2, 3):
         for t in ("f32", "f64"):
             out.add(f"ipx_eval{d}d_{t}")
+    # macro-generated derivative entry points (IPX_DECL_GRAD)
+    for t in ("f32", "f64"):
+        out.add(f"ipx_vjp_stencil_{t}")
+        out.add(f"ipx_jvp_stencil_{t}")
     return {n for n in out if not n.startswith("ipx_eval") or re.fullmatch(r"ipx_eval([123]d|_stencil)_f(32|64)", n)}
 
 
