@@ -232,7 +232,31 @@ __device__ __forceinline__ void linear_weights(const AxisLoc<T>& L, int order, T
 // ------------------------------------------------------------------------------------
 // rare paths kept out of line (values in and out through registers only): the hot loop must
 // stay small for the instruction caches
-template <typename T> __device__ __noinline__ T py_mod_slow(T q, T P) { return py_mod(q, P); }
+//
+// Remainder of a query that is more than one period out.  fmod is a long software loop on the
+// GPU; for a quotient small enough that floor(q / P) is off by at most one, the same value comes
+// from one division and one fused multiply-add: q - k P is formed exactly inside the fma and
+// rounded once, which is what fmod (exact) followed by the Python sign fix-up (+ P, one rounding)
+// produces.  An estimate one too large shows as r < 0, one too small as r >= P -- except that a
+// tiny negative q legitimately rounds up to r == P, told apart by trying k + 1.  Everything else
+// (huge quotients, NaN, inf, P == 0) keeps the fmod path.
+template <typename T> __device__ __forceinline__ T quotient_limit();
+template <> __device__ __forceinline__ float quotient_limit<float>() { return 1048576.f; }        // 2^20
+template <> __device__ __forceinline__ double quotient_limit<double>() { return 2147483648.0; }   // 2^31
+template <typename T> __device__ __noinline__ T py_mod_slow(T q, T P) {
+  const T k = floor(q / P);
+  if (fabs(k) < quotient_limit<T>()) {
+    T r = fma(-k, P, q);
+    if (r < T(0)) {
+      r = fma(-(k - T(1)), P, q);
+    } else if (r >= P) {
+      const T r2 = fma(-(k + T(1)), P, q);
+      if (r2 >= T(0)) r = r2;
+    }
+    return r;
+  }
+  return py_mod(q, P);
+}
 template <typename T>
 __device__ __noinline__ int bin_index_slow(const T* x, int n, T q, T x_first, T inv_h) {
   T lo, hi;

@@ -1149,3 +1149,46 @@ def test_unaligned_out_and_odd_counts(dtype):
             assert torch.equal(torch.nan_to_num(ret, nan=-7.0), torch.nan_to_num(want, nan=-7.0)), (nq, off)
             # nothing written outside the window
             assert torch.all(buf[:off] == -5.0) and torch.all(buf[off + nq:] == -5.0), (nq, off)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("ndim", [1, 2, 3])
+def test_queries_many_periods_out_wrap_to_the_same_bits(ndim, dtype):
+    """Periodic axes: a query any number of periods out goes through the out-of-line remainder
+    (one division + one fma while the quotient is small, fmod beyond that).  Its result must be
+    the Python remainder bit for bit (the reference wraps with `xq % period`, _spline.py:217):
+    evaluating q and evaluating np.mod(q, P) -- already inside [0, P), where the kernels do not
+    touch the value -- must give identical bits, in the cooperative kernels (many queries) and
+    the one-thread-per-query kernel (few)."""
+    rng = np.random.default_rng(100 + ndim)
+    n = 12
+    P = [np.dtype(dtype).type(2 * np.pi), np.dtype(dtype).type(1.3), np.dtype(dtype).type(0.1)][:ndim]
+    knots = [np.linspace(0, float(p), n, endpoint=False).astype(dtype) for p in P]
+    f = rng.normal(size=(n,) * ndim).astype(dtype)
+    cls = (ipx.Interpolator1D, ipx.Interpolator2D, ipx.Interpolator3D)[ndim - 1]
+    period = P[0] if ndim == 1 else tuple(P)
+    for method in ("cubic", "cubic2", "linear"):
+        ip = cls(*knots, f, method, True, period)
+        for nq in (300, 70_000):
+            q = []
+            for p in P:
+                span = rng.choice([1.5, 3.0, 40.0, 3e4 if dtype == np.float64 else 900.0], nq)
+                v = rng.uniform(-1, 1, nq) * span * float(p)
+                k = rng.integers(-60, 60, nq)
+                edge = (k * p.astype(np.float64)).astype(dtype)
+                v = np.where(rng.random(nq) < 0.05, edge, v.astype(dtype))
+                v = np.where(rng.random(nq) < 0.02, np.nextafter(edge, dtype(np.inf)), v)
+                v = np.where(rng.random(nq) < 0.02, np.nextafter(edge, dtype(-np.inf)), v)
+                v[:4] = [1e15, -1e15, 3e30, -7e29]      # quotients beyond the fast path
+                q.append(v.astype(dtype))
+            r = [np.mod(v, p) for v, p in zip(q, P)]
+            assert all(a.dtype == dtype for a in r)
+            # a remainder that rounds up to P itself would wrap once more on the second pass
+            keep = np.ones(nq, dtype=bool)
+            for a, p in zip(r, P):
+                keep &= a < p
+            got = np.asarray(ip(*q))
+            want = np.asarray(ip(*r))
+            assert keep.sum() > 0.9 * nq
+            assert np.array_equal(got[keep], want[keep]), (ndim, method, nq,
+                                                           np.flatnonzero(got[keep] != want[keep])[:5])
