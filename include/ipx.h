@@ -195,6 +195,7 @@ IPX_DECL_EVAL(f64, double)
 #define IPX_STENCIL_AUTO 0
 #define IPX_STENCIL_SPARSE 1
 #define IPX_STENCIL_DENSE 2
+#define IPX_STENCIL_COLUMN 3
 /* elements of the halo table (the last axis is padded to a multiple of 32 bytes), or -1 */
 int64_t ipx_halo_table_elems(int32_t ndim, const int32_t* n, int32_t periodic_mask, int32_t elem_size);
 int ipx_halo_table_f32(int32_t ndim, const float* f, const int32_t* n, int32_t periodic_mask,

@@ -20,7 +20,7 @@ IPX_SLOPE_MONOTONIC, IPX_SLOPE_MONOTONIC0, IPX_SLOPE_AKIMA, IPX_SLOPE_ZERO = 3, 
 IPX_SLOPE_AKIMA_COMPLEX = 7
 IPX_PPOLY_NAN, IPX_PPOLY_EXTRAPOLATE, IPX_PPOLY_PERIODIC = 0, 1, 2
 IPX_BC_NOT_A_KNOT, IPX_BC_FIRST, IPX_BC_SECOND = 0, 1, 2
-IPX_STENCIL_AUTO, IPX_STENCIL_SPARSE, IPX_STENCIL_DENSE = 0, 1, 2
+IPX_STENCIL_AUTO, IPX_STENCIL_SPARSE, IPX_STENCIL_DENSE, IPX_STENCIL_COLUMN = 0, 1, 2, 3
 
 
 def IPX_PERIODIC(axis: int) -> int:

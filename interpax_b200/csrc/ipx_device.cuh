@@ -279,11 +279,10 @@ template <typename T> __device__ __forceinline__ T wrap_one_period(T v, T Pd, bo
   return r;
 }
 
-// cubic Hermite weights from the local coordinate pieces (same formulas as hermite_weights)
+// cubic Hermite weights from the local coordinate t, the cell width dx and its reciprocal
+// (same formulas as hermite_weights)
 template <typename T, bool ORD0>
-__device__ __forceinline__ void hermite_weights_r(T q, T x0, T x1, int order, T dxi, T w[4]) {
-  T dx = x1 - x0;
-  T t = (q - x0) * dxi;
+__device__ __forceinline__ void hermite_weights_t(T t, T dx, T dxi, int order, T w[4]) {
   T tt0, tt1, tt2, tt3;
   if (ORD0 || order <= 0) {
     tt0 = T(1); tt1 = t; tt2 = t * t; tt3 = tt2 * t;
@@ -302,6 +301,10 @@ __device__ __forceinline__ void hermite_weights_r(T q, T x0, T x1, int order, T 
   w[1] = T(3) * tt2 - T(2) * tt3;
   w[2] = (tt1 - T(2) * tt2 + tt3) * dx;
   w[3] = (tt3 - tt2) * dx;
+}
+template <typename T, bool ORD0>
+__device__ __forceinline__ void hermite_weights_r(T q, T x0, T x1, int order, T dxi, T w[4]) {
+  hermite_weights_t<T, ORD0>((q - x0) * dxi, x1 - x0, dxi, order, w);
 }
 
 // ------------------------------------------------------------------------------------

@@ -230,17 +230,24 @@ template <typename T> struct Taps4 {
 // stencil coefficients of the cell's two knots.  Out of line: the hot loops only call it for
 // the cells that are not regular (one-sided ends, non-uniform knots, cardinal tension, orders >= 2).
 template <typename T>
-__device__ __noinline__ Taps4<T> st_taps_general(const T* __restrict__ ks, const Coef2<T>* __restrict__ ac, int i,
-                                                 T l, T r, T v, int order) {
+__device__ __noinline__ Taps4<T> st_taps_general_t(const T* __restrict__ ks, const Coef2<T>* __restrict__ ac, int i,
+                                                   T t, T rabs, int order) {
   const Coef2<T> L = ac[i - 1], R = ac[i];
   T w[4];
-  hermite_weights_r<T, false>(v, l, ks[i], order, t_abs(r), w);
+  hermite_weights_t<T, false>(t, ks[i] - ks[i - 1], rabs, order, w);
   Taps4<T> o;
   o.t0 = w[2] * L.a;
   o.t1 = fma(w[3], R.a, fma(w[2], -(L.a + L.c), w[0]));
   o.t2 = fma(w[3], -(R.a + R.c), fma(w[2], L.c, w[1]));
   o.t3 = w[3] * R.c;
   return o;
+}
+// (l = ks[i-1]; one out-of-line body for every kernel shape, so the shapes agree bit for bit)
+template <typename T>
+__device__ __forceinline__ Taps4<T> st_taps_general(const T* __restrict__ ks, const Coef2<T>* __restrict__ ac, int i,
+                                                    T l, T r, T v, int order) {
+  const T rabs = t_abs(r);
+  return st_taps_general_t<T>(ks, ac, i, (v - l) * rabs, rabs, order);
 }
 
 // regular cells only (the dense kernel's hot loop; it redoes everything else out of line)
@@ -1058,6 +1065,10 @@ static bool st_grant_smem(const void* kern, int dev, size_t smem) {
   return true;
 }
 
+}  // namespace ipx
+#include "ipx_stencil_col.cuh"
+namespace ipx {
+
 template <typename T, int ND, int TAPS, int WM>
 static void (*st_dense_entry(const StArgs<T, ND>& a, bool ord0))(const StArgs<T, ND>) {
   return a.dp ? stencil_dense_kernel<T, ND, TAPS, true, false, WM>
@@ -1150,7 +1161,7 @@ static int launch_stencil(const T* const* q, int64_t nq, const T* const* knots, 
                           int32_t* idx_out, int32_t hint, int32_t* workspace, void* stream) {
   if (nq < 0 || q == nullptr || knots == nullptr || n == nullptr || params == nullptr) return IPX_EINVAL;
   if (slope_method != IPX_SLOPE_CUBIC && slope_method != IPX_SLOPE_CARDINAL) return IPX_EUNSUPPORTED;
-  if (hint < IPX_STENCIL_AUTO || hint > IPX_STENCIL_DENSE) return IPX_EINVAL;
+  if (hint < IPX_STENCIL_AUTO || hint > IPX_STENCIL_COLUMN) return IPX_EINVAL;
   if (nq == 0) return IPX_OK;
   if (out == nullptr || halo == nullptr) return IPX_EINVAL;
   StArgs<T, ND> a;
@@ -1214,6 +1225,12 @@ static int launch_stencil(const T* const* q, int64_t nq, const T* const* knots, 
   // (The dense shape does not write interval indices: such calls run the sparse shape.)
   const bool dense_ok = idx_out == nullptr && low_order;
   if (hint == IPX_STENCIL_DENSE && dense_ok) return st_launch_q<T, ND, true, IPX_STENCIL_TAPS>(a, d, s);
+  if constexpr (ND == 3) {
+    if (hint == IPX_STENCIL_COLUMN && dense_ok) {
+      const int rc = st_launch_column<T>(a, d, s);
+      if (rc != IPX_EUNSUPPORTED) return rc;
+    }
+  }
   if (hint != IPX_STENCIL_AUTO || workspace == nullptr || idx_out != nullptr || nq < (1 << 16))
     return st_launch_q<T, ND, false, 4>(a, d, s);
 

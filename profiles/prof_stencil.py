@@ -56,14 +56,15 @@ ipr = mk(**ipa.derivs) if "records" in what else None  # records only
 ip = mk()  # halo only
 ip._tabs = ip._packed = None
 torch.cuda.synchronize()
-HINTS = {"dense": L.IPX_STENCIL_DENSE, "sparse": L.IPX_STENCIL_SPARSE, "auto": L.IPX_STENCIL_AUTO}
+HINTS = {"dense": L.IPX_STENCIL_DENSE, "sparse": L.IPX_STENCIL_SPARSE, "auto": L.IPX_STENCIL_AUTO,
+         "column": L.IPX_STENCIL_COLUMN}
 ref = {}
 for d in deriv:
     for stream, sname in ((sq, "sorted"), (qs, "random")):
         for w in what:
             obj = ipr if w == "records" else (ipa if w == "full" else ip)
             api.stencil_hint = HINTS.get(w, L.IPX_STENCIL_AUTO)
-            if w == "dense" and sname == "random" and nq > 20_000_000:
+            if w in ("dense", "column") and sname == "random" and nq > 20_000_000:
                 continue  # every slot through the redo path: slow by construction
             ts = []
             for rep in range(reps):

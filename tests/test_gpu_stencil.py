@@ -103,7 +103,8 @@ def test_stencil_shapes_vs_oracle(ndim, method, dtype):
                 assert ip._halo is not None, what
             res_f, res_c = {}, {}
             for name, h, stream in (("sparse", L.IPX_STENCIL_SPARSE, qs), ("dense", L.IPX_STENCIL_DENSE, qs),
-                                    ("dense-sorted", L.IPX_STENCIL_DENSE, qsorted), ("auto", L.IPX_STENCIL_AUTO, qsorted)):
+                                    ("dense-sorted", L.IPX_STENCIL_DENSE, qsorted), ("auto", L.IPX_STENCIL_AUTO, qsorted),
+                                    ("column", L.IPX_STENCIL_COLUMN, qs), ("column-sorted", L.IPX_STENCIL_COLUMN, qsorted)):
                 with hint(h):
                     gf = gfun(*stream, *knots, f, method, dfun, extrap, period, **kw)
                     gc = ip(*stream, *deriv)
@@ -117,7 +118,7 @@ def test_stencil_shapes_vs_oracle(ndim, method, dtype):
                 res_f[name], res_c[name] = gf, gc
                 assert_parity(gf, want_f, f"functional {name} {what}", truth_f)
                 assert_parity(gc, want_c, f"class {name} {what}", truth_c)
-            for name in ("dense", "dense-sorted", "auto"):
+            for name in ("dense", "dense-sorted", "auto", "column", "column-sorted"):
                 assert same_bits(res_f[name], res_f["sparse"]), f"functional {name} {what}"
                 assert same_bits(res_c[name], res_c["sparse"]), f"class {name} {what}"
 
@@ -173,8 +174,11 @@ def test_stencil_non_finite_table_entries(dtype):
         sparse = ipx.interp3d(*qsorted, *knots, f, "cubic")
     with hint(L.IPX_STENCIL_DENSE):
         dense = ipx.interp3d(*qsorted, *knots, f, "cubic")
+    with hint(L.IPX_STENCIL_COLUMN):
+        column = ipx.interp3d(*qsorted, *knots, f, "cubic")
     assert np.isnan(sparse).any() and (~np.isnan(sparse)).any()
     assert same_bits(dense, sparse)
+    assert same_bits(column, sparse)
     # against the record form of the reference's arithmetic: same set of non-finite results
     sel = np.linspace(0, nq - 1, 8000).astype(np.int64)
     # (float32: compare with the float64 evaluation of the same float32 inputs -- the float32
@@ -221,6 +225,14 @@ def test_stencil_full_size_c4_dense_vs_sparse():
     with hint(L.IPX_STENCIL_SPARSE):
         sparse = ip(xq, yq, zq)
         sparse_dx = ip(xq, yq, zq, 1, 0, 0)
+    with hint(L.IPX_STENCIL_COLUMN):
+        column = ip(xq, yq, zq)
+        column_dx = ip(xq, yq, zq, 1, 0, 0)
+        # an unsorted stream through the same shape: every window falls back to the one-query path
+        perm = torch.randperm(1 << 18, device=dev, generator=g)
+        column_rand = ip(xq[perm], yq[perm], zq[perm])
+    assert torch.equal(column, sparse) and torch.equal(column_dx, sparse_dx)
+    assert torch.equal(column_rand, sparse[perm])
     auto = ip(xq, yq, zq)
     assert torch.equal(dense, sparse) and torch.equal(dense_dx, sparse_dx) and torch.equal(auto, sparse)
     assert torch.all(dense[zq > 1.0] == 0.0) and torch.isfinite(dense).all()
