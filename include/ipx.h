@@ -182,7 +182,10 @@ IPX_DECL_EVAL(f64, double)
  *   than L2, and in 2-D).
  *   hint: IPX_STENCIL_SPARSE = one query per lane; IPX_STENCIL_DENSE = four consecutive queries per
  *   lane share the table rows, staged in shared memory (for cell-sorted streams with several
- *   queries per cell; any stream is still evaluated correctly); IPX_STENCIL_AUTO chooses, and if
+ *   queries per cell; any stream is still evaluated correctly); IPX_STENCIL_COLUMN (3-D only; other
+ *   ranks run the sparse shape) = the rows of the CTA's cell columns staged in shared memory by bulk
+ *   copies, queries re-paired by cell so a lane reads the 4^3 neighbourhood once for two queries (for
+ *   dense cell-sorted streams; any stream is still evaluated correctly); IPX_STENCIL_AUTO chooses, and if
  *   `workspace` (NULL, or 4 int32 of device scratch) is given it chooses ON THE DEVICE: a probe
  *   kernel classifies a sample of the stream (dense cell-sorted / cell-sorted / random), every
  *   candidate kernel is enqueued and the ones not chosen return at once -- no host

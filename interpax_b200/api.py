@@ -420,6 +420,7 @@ def _eval_dev(ndim, qs, knots, perms, ns, tables, layout, batch, method_class, p
 # methods whose slope chain is a linear three-point stencil along one axis: evaluated straight
 # from f by ipx_eval_stencil_* (no slope tables, no records): name -> slope code
 _STENCIL_METHODS = {"cubic": L.IPX_SLOPE_CUBIC, "cardinal": L.IPX_SLOPE_CARDINAL, "catmull-rom": L.IPX_SLOPE_CARDINAL}
+_FAST_CALL_MAX = 1 << 16  # queries: larger calls need the device-side choice of kernel (scratch) anyway
 _STENCIL_SMEM = 227 * 1024 - 4096  # what the knots + coefficients of all axes may take per CTA
 stencil_hint = L.IPX_STENCIL_AUTO  # experiments / benchmarks: force a kernel shape
 
@@ -731,12 +732,15 @@ def _interp(ndim, qs, knots, f, method, derivative, extrap, period, kwargs, retu
         sns = [tabs["f"].shape[ax] for ax in range(ndim)]
         code = _STENCIL_METHODS[method]
         cten = float(kwargs.get("c", 0)) if method == "cardinal" else 0.0
-        # several queries per cell: the records of the (padded) table as well, one fused pass; the
-        # device then picks the faster form for the stream it sees (dense cell-sorted 3-D streams)
+        # 2-D, several queries per cell: the records of the (padded) table as well, one fused pass; the
+        # device then picks the faster form for the stream it sees (random order).  In 3-D the
+        # records are not worth building per call: dense cell-sorted streams run the column shape
+        # of the evaluation from f (2.2 ms per 1e8 queries on 256^3 against 1.9 ms on records that
+        # take 0.5 ms to build)
         recs = None
         nq_total = int(np.prod([int(v) for v in np.broadcast_shapes(*[_shape(q) for q in qs])], dtype=np.int64))
         cells = float(np.prod([max(1, int(k.shape[0]) - 1) for k in sk], dtype=np.float64))
-        if ndim >= 2 and nq_total >= 3.0 * cells and nq_total >= (1 << 16):
+        if ndim == 2 and nq_total >= 3.0 * cells and nq_total >= (1 << 16):
             ftab = tabs["f"]
             for ax in range(ndim):
                 if per[ax]:
@@ -1081,6 +1085,7 @@ class _InterpolatorND:
         self._packed = None
         self._tabs = None
         self._halo = None
+        self._plans = {}  # derivative orders -> call plan of small device-resident calls (_fast_call)
         if (method in _STENCIL_METHODS and self._batch == 1 and not io.complex
                 and all(v is None for v in given.values())):
             # linear three-point stencils on a scalar table: evaluate straight from f (one padded
@@ -1150,9 +1155,64 @@ class _InterpolatorND:
             self._pk_cache[key] = (xpad, perm)
         return self._pk_cache[key]
 
+    def _fast_call(self, plan, qs, out):
+        """A small call with device tensors of the stored type (the README case: 1e4 queries),
+        where Python and ctypes -- not the kernel -- are the cost: every argument that does not
+        depend on the queries was converted once (`plan`); only the pointers, the count and the
+        result are new.  Returns None if the call is not of that kind."""
+        q0 = qs[0]
+        tdt, dev = plan["tdt"], plan["dev"]
+        if type(q0) is not torch.Tensor or q0.dtype != tdt or q0.device != dev or not q0.is_contiguous():
+            return None
+        shape = q0.shape
+        nq = q0.numel()
+        if nq == 0 or nq >= _FAST_CALL_MAX:
+            return None
+        ndim = self._ndim
+        qarr = (C.c_void_p * ndim)()
+        qarr[0] = q0.data_ptr()
+        for k in range(1, ndim):
+            q = qs[k]
+            if type(q) is not torch.Tensor or q.dtype != tdt or q.device != dev or q.shape != shape or not q.is_contiguous():
+                return None
+            qarr[k] = q.data_ptr()
+        if out is None:
+            res = torch.empty(shape, dtype=tdt, device=dev)
+        else:
+            if (type(out) is not torch.Tensor or out.dtype != tdt or out.device != dev or out.numel() != nq
+                    or not out.is_contiguous()):
+                return None
+            res = out
+        a = plan["args"]
+        rc = plan["fn"](a[0], qarr, nq, a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], 0, res.data_ptr(), None,
+                        stencil_hint, None, _stream())
+        if rc != 0:
+            return None  # (the general path reports the error, or falls back to the record form)
+        return res if out is None else res.view(shape)
+
+    def _make_plan(self, derivative, kuse, ns, mask, params):
+        """Plan of `_fast_call` for these derivative orders (evaluation from f, scalar real table)."""
+        ndim = self._ndim
+        keep = (_ptr_array(kuse), _ptr_array(self._knots), (C.c_int32 * ndim)(*[int(n) for n in ns]), params,
+                list(kuse), self._halo, self._packed)
+        cten = float(self._kwargs.get("c", 0)) if self.method == "cardinal" else 0.0
+        return {
+            "tdt": self._io.tdt, "dev": self._f.device, "keep": keep,
+            "fn": getattr(L.load(), f"ipx_eval_stencil_{_suffix(self._f)}"),
+            "args": (ndim, keep[0], keep[1], keep[2], self._halo.data_ptr(),
+                     None if self._packed is None else self._packed.data_ptr(), _STENCIL_METHODS[self.method], cten,
+                     mask, C.byref(params)),
+        }
+
     def _call(self, qs, derivative, out=None, return_index=False, presort=False):
         ndim = self._ndim
         st = self._io
+        if not return_index and not presort and self._plans:
+            plan = self._plans.get(tuple(derivative))
+            if plan is not None:
+                res = self._fast_call(plan, qs, out)
+                if res is not None:
+                    return res
         # promotion of the call mirrors interpNd(xq, self.x, self.f, ...)
         io = _Inputs(qs, [np.zeros((), st.xdt)], None, stored=st)
         if io.rdt != st.rdt:
@@ -1203,11 +1263,16 @@ class _InterpolatorND:
                 if res is not None:
                     return res
                 self._halo = None  # knot vectors too long for shared memory: record form from now on
+                self._plans.clear()
             return launch_records(dq, dout, want_idx)
 
         if presort:
             launch = _presorted(launch, ndim, kuse, ns, mask, params, batch)
-        return _execute(io, qs, launch, batch, self._fshape[ndim:], out, return_index)
+        res = _execute(io, qs, launch, batch, self._fshape[ndim:], out, return_index)
+        if (self._halo is not None and not st.complex and io.want_torch and len(self._plans) < 16
+                and all(isinstance(d, (int, np.integer)) for d in derivative)):
+            self._plans.setdefault(tuple(derivative), self._make_plan(derivative, kuse, ns, mask, params))
+        return res
 
 
 class Interpolator1D(_InterpolatorND):

@@ -229,25 +229,53 @@ template <typename T> struct Taps4 {
 // any cell, any derivative order: Hermite weights of _get_t_der . A_CUBIC composed with the
 // stencil coefficients of the cell's two knots.  Out of line: the hot loops only call it for
 // the cells that are not regular (one-sided ends, non-uniform knots, cardinal tension, orders >= 2).
+// (Every operation below is an explicit round-to-nearest multiply, add or fused multiply-add, so
+// the compiler cannot contract or reassociate it differently from one inlining context to the
+// next: the out-of-line copy the sparse / dense shapes call and the inlined copy in the column
+// shape's hot loop give the same bits.)
+template <typename T>
+__device__ __forceinline__ Taps4<T> st_taps_general_inl(const T* __restrict__ ks, const Coef2<T>* __restrict__ ac,
+                                                        int i, T t, T rabs, int order) {
+  const Coef2<T> L = ac[i - 1], R = ac[i];
+  const T dx = add_rn(ks[i], -ks[i - 1]);
+  const T dxi = rabs;
+  T tt0, tt1, tt2, tt3;
+  if (order <= 0) {
+    tt0 = T(1); tt1 = t; tt2 = mul_rn(t, t); tt3 = mul_rn(tt2, t);
+  } else if (order == 1) {
+    tt0 = T(0); tt1 = dxi; tt2 = mul_rn(mul_rn(T(2), t), dxi); tt3 = mul_rn(mul_rn(T(3), mul_rn(t, t)), dxi);
+  } else if (order == 2) {
+    const T s2 = mul_rn(dxi, dxi);
+    tt0 = T(0); tt1 = T(0); tt2 = mul_rn(T(2), s2); tt3 = mul_rn(mul_rn(T(6), t), s2);
+  } else if (order == 3) {
+    tt0 = T(0); tt1 = T(0); tt2 = T(0); tt3 = mul_rn(T(6), mul_rn(mul_rn(dxi, dxi), dxi));
+  } else {
+    const T z = mul_rn(dxi, T(0));
+    tt0 = z; tt1 = z; tt2 = z; tt3 = z;
+  }
+  // tt . A_CUBIC (columns [[1,0,0,0],[0,0,1,0],[-3,3,-2,-1],[2,-2,1,1]]), slope weights times dx
+  const T w0 = fma(T(2), tt3, fma(T(-3), tt2, tt0));
+  const T w1 = fma(T(-2), tt3, mul_rn(T(3), tt2));
+  const T w2 = mul_rn(add_rn(fma(T(-2), tt2, tt1), tt3), dx);
+  const T w3 = mul_rn(add_rn(tt3, -tt2), dx);
+  Taps4<T> o;
+  o.t0 = mul_rn(w2, L.a);
+  o.t1 = fma(w3, R.a, fma(w2, -add_rn(L.a, L.c), w0));
+  o.t2 = fma(w3, -add_rn(R.a, R.c), fma(w2, L.c, w1));
+  o.t3 = mul_rn(w3, R.c);
+  return o;
+}
 template <typename T>
 __device__ __noinline__ Taps4<T> st_taps_general_t(const T* __restrict__ ks, const Coef2<T>* __restrict__ ac, int i,
                                                    T t, T rabs, int order) {
-  const Coef2<T> L = ac[i - 1], R = ac[i];
-  T w[4];
-  hermite_weights_t<T, false>(t, ks[i] - ks[i - 1], rabs, order, w);
-  Taps4<T> o;
-  o.t0 = w[2] * L.a;
-  o.t1 = fma(w[3], R.a, fma(w[2], -(L.a + L.c), w[0]));
-  o.t2 = fma(w[3], -(R.a + R.c), fma(w[2], L.c, w[1]));
-  o.t3 = w[3] * R.c;
-  return o;
+  return st_taps_general_inl<T>(ks, ac, i, t, rabs, order);
 }
 // (l = ks[i-1]; one out-of-line body for every kernel shape, so the shapes agree bit for bit)
 template <typename T>
 __device__ __forceinline__ Taps4<T> st_taps_general(const T* __restrict__ ks, const Coef2<T>* __restrict__ ac, int i,
                                                     T l, T r, T v, int order) {
   const T rabs = t_abs(r);
-  return st_taps_general_t<T>(ks, ac, i, (v - l) * rabs, rabs, order);
+  return st_taps_general_t<T>(ks, ac, i, mul_rn(add_rn(v, -l), rabs), rabs, order);
 }
 
 // regular cells only (the dense kernel's hot loop; it redoes everything else out of line)
@@ -1236,7 +1264,7 @@ static int launch_stencil(const T* const* q, int64_t nq, const T* const* knots, 
 
   // ---- automatic choice, on the device.  Measured on B200 (profiles/stencil_r02.jsonl):
   //   dense cell-sorted stream   3-D: tile kernel on the records (if the caller has them), else the
-  //                              dense shape; 1-D / 2-D: the dense shape
+  //                              column shape (ipx_stencil_col.cuh); 1-D / 2-D: the dense shape
   //   cell-sorted, sparse        the sparse shape (rows shared through L1)
   //   random order               table about L2-sized or smaller, 3-D: the sparse shape (8x fewer
   //                              bytes than the records); larger tables, and 2-D (same bytes,
@@ -1248,12 +1276,18 @@ static int launch_stencil(const T* const* q, int64_t nq, const T* const* knots, 
   // (the tile kernel on the records overtakes the sparse shape between three and six queries per
   // cell: 256^3 f64, 5e7 queries 1.73 vs 1.44 ms, 1e8 queries 1.86 vs 2.83 ms)
   const bool rec_quads = records != nullptr && ND == 3 && dense_ok && (double)nq >= 4.0 * cells;
-  if (!dense && !rec_random && !rec_quads) return st_launch_q<T, ND, false, 4>(a, d, s);  // one candidate: no probe
+  // (without records, dense cell-sorted 3-D streams go to the column shape: 2.2 vs 2.8 ms)
+  bool col_quads = false;
+  if constexpr (ND == 3) {
+    ColPlan pl;
+    col_quads = !rec_quads && dense_ok && (double)nq >= 4.0 * cells && st_column_plan<T>(a, d, pl);
+  }
+  if (!dense && !rec_random && !rec_quads && !col_quads) return st_launch_q<T, ND, false, 4>(a, d, s);  // one candidate: no probe
   stencil_probe_kernel<T, ND, IPX_STENCIL_TAPS><<<1, 256, 0, s>>>(a, workspace);
   count_launches(1);
   a.flag = workspace;
   uint32_t sparse_accept = 1u << IPX_STREAM_LOCAL;
-  if (!dense && !rec_quads) sparse_accept |= 1u << IPX_STREAM_QUADS;
+  if (!dense && !rec_quads && !col_quads) sparse_accept |= 1u << IPX_STREAM_QUADS;
   if (!rec_random) sparse_accept |= 1u << IPX_STREAM_RANDOM;
   uint32_t rec_accept = (rec_random ? 1u << IPX_STREAM_RANDOM : 0u) | (rec_quads ? 1u << IPX_STREAM_QUADS : 0u);
   int rc = IPX_OK;
@@ -1261,6 +1295,13 @@ static int launch_stencil(const T* const* q, int64_t nq, const T* const* knots, 
     a.accept = 1u << IPX_STREAM_QUADS;
     rc = st_launch_q<T, ND, true, IPX_STENCIL_TAPS>(a, d, s);
     if (rc != IPX_OK) return rc;
+  }
+  if constexpr (ND == 3) {
+    if (col_quads) {
+      a.accept = 1u << IPX_STREAM_QUADS;
+      rc = st_launch_column<T>(a, d, s);
+      if (rc != IPX_OK) return rc;
+    }
   }
   a.accept = sparse_accept;
   rc = st_launch_q<T, ND, false, 4>(a, d, s);

@@ -16,19 +16,21 @@
 //     cells), and stages the 4 x (K+3) table rows those columns read -- each row one
 //     cp.async.bulk of the full last-axis extent -- into one of two row buffers, completing on an
 //     mbarrier (full[b]); consumer warps hand the buffer back through free[b].
-//   * A consumer warp takes a contiguous share of the window, 64 queries per round (two per lane),
-//     locates them (phase 1), and RE-PAIRS them: consecutive queries of one cell form a pair, a
-//     pair takes a lane (a cell with an odd count leaves one half empty).  Local coordinates and
-//     cell indices travel through a 2 KB per-warp exchange buffer; queries that do not fit the
-//     32 lanes are simply read again next round (the cursor advances by what was taken).
-//   * Phase 2: each lane forms the taps of its pair and walks the 16 rows of the cell: four
-//     8-byte shared-memory loads at immediate offsets from one base register per row, applied to
-//     both queries.  Operand delivery per query halves; there is no address arithmetic per row.
+//   * The consumer warps take the window's rounds of 64 consecutive queries in turn, two
+//     CONSECUTIVE queries per lane.  In a dense cell-sorted stream the second query of a lane sits
+//     in the first one's cell or in the next cell up the last axis; the lane then reads FIVE
+//     values per row -- 8-byte shared-memory loads at immediate offsets from one base register --
+//     and applies them to both queries, the second with its four taps shifted by the cell
+//     distance (a zero fifth tap).  Operand delivery per query drops from 64 to 40 loads and
+//     there is no grouping, no copy loop and no address arithmetic per row.  A second query that
+//     does not ride (other column, further away) takes a second pass of the same code.
 //
-// Queries the hot path does not cover -- irregular cells (st_stage), derivative orders above 1,
-// a failed interval guess, cells outside the staged columns (an unsorted stream) -- go through
-// the one-query path (st_redo), so results never depend on the stream order or the neighbours:
-// the arithmetic of a query is st_eval_one's, operation for operation (bitwise equal, tested).
+// Queries the hot path does not cover -- a failed interval guess, queries more than a period out,
+// cells outside the staged columns (an unsorted stream), NaN results (a non-finite table entry
+// under the zero tap, or a NaN query) -- go through the one-query path (st_redo), so results never
+// depend on the stream order or the neighbours: the arithmetic of a query is st_eval_one's,
+// operation for operation (bitwise equal, tested).  Irregular cells (st_stage) and derivative
+// orders above 1 use the general taps (st_taps_general_inl) in line.
 #pragma once
 #include <type_traits>
 
@@ -38,13 +40,11 @@ namespace ipx {
 #define IPX_COL_WARPS 15
 #endif
 constexpr int kColWarps = IPX_COL_WARPS;   // consumer warps; one more warp produces
-constexpr int kColSub = 640;    // most queries per consumer warp and window
-constexpr int kColStep = kColWarps * kColSub / 32;  // spacing of the producer's probes
+constexpr int kColStep = 320;   // spacing of the producer's probes: a window is at most 31 steps, whole rounds
 constexpr int kColMaxSegs = 8;  // stream segments per CTA (interleaved over the CTAs)
 
 template <typename T> struct ColCfg {
-  static constexpr int TQ_BYTES = 3 * 64 * (int)sizeof(T);   // local coordinates of 64 entries
-  static constexpr int XCH_BYTES = TQ_BYTES + 64 * 8;        // + 8 bytes of cell / flags each
+  static constexpr int XCH_BYTES = 3 * 64 * (int)sizeof(T);  // per warp: the next round's coordinates
 };
 
 // one cell of one axis as phase 1 reads it: lower knot and signed reciprocal width (st_stage)
@@ -72,6 +72,19 @@ __device__ __forceinline__ bool col_mbar_test(unsigned mbar_s, unsigned phase) {
       : "r"(mbar_s), "r"(phase)
       : "memory");
   return ok != 0;
+}
+// blocking wait: try_wait with a suspend-time hint parks the warp in hardware until the phase
+// completes (or the hint, about 10 ms, runs out) instead of polling
+__device__ __forceinline__ void col_mbar_wait(unsigned mbar_s, unsigned phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "IPX_COL_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra IPX_COL_DONE;\n"
+      "bra IPX_COL_WAIT;\n"
+      "IPX_COL_DONE:\n"
+      "}\n" ::"r"(mbar_s), "r"(phase), "r"(0x989680u) : "memory");
 }
 __device__ __forceinline__ void col_mbar_arrive(unsigned mbar_s) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(mbar_s) : "memory");
@@ -112,8 +125,10 @@ __device__ __forceinline__ bool col_inside(float t) { return (unsigned)__float_a
 
 // shared memory after the knot tables: [cells of the 3 axes][exchange buffers][row buffer 0][row buffer 1]
 // WM: set of axes whose queries are wrapped, as a compile-time mask (-1: read the flags).
+// registers per thread: what one CTA of kColWarps + 1 warps per SM leaves (multiple of 8)
+constexpr int kColRegs = (65536 / ((kColWarps + 1) * 32)) / 8 * 8 > 255 ? 255 : (65536 / ((kColWarps + 1) * 32)) / 8 * 8;
 template <typename T, bool DEVP, bool ORD0, int WM>
-__global__ void __launch_bounds__((kColWarps + 1) * 32, 1)
+__global__ void __maxnreg__(kColRegs)
 stencil_column_kernel(const __grid_constant__ StArgs<T, 3> a, const int ry, const int rs, const int nseg, const int seg) {
   constexpr int ND = 3;
   using Cfg = ColCfg<T>;
@@ -123,6 +138,7 @@ stencil_column_kernel(const __grid_constant__ StArgs<T, 3> a, const int ry, cons
   __shared__ ipx_params params_s;
   __shared__ __align__(16) ColHdr HDR[2];
   __shared__ __align__(8) unsigned long long MBAR[4];  // full[0], full[1], free[0], free[1]
+  __shared__ int NEXT_ROUND[2];  // per row buffer: the next round of its window nobody has taken yet
   if (a.flag != nullptr && ((a.accept >> (*a.flag & 31)) & 1u) == 0) return;
   if (DEVP && threadIdx.x == 32) params_s = *a.dp;
   const ipx_params& P = DEVP ? params_s : a.hp;
@@ -137,27 +153,25 @@ stencil_column_kernel(const __grid_constant__ StArgs<T, 3> a, const int ry, cons
   st_stage<T, ND>(a, smem, AXC, S);  // (ends with a barrier: the mbarriers are initialised too)
   const int tables = st_layout<T, ND>(a).total;
   // per axis, cell i as one 16-byte (float: 8-byte) entry {ks[i-1], rr[i]}
-  const ColCell<T>* CELL[ND];
   {
     int off = tables;
 #pragma unroll
     for (int ax = 0; ax < ND; ++ax) {
       ColCell<T>* cl = reinterpret_cast<ColCell<T>*>(smem + off);
-      CELL[ax] = cl;
       const int nk = a.ax[ax].nk;
-      for (int i = threadIdx.x; i < nk; i += (int)blockDim.x) {
+      for (int i = threadIdx.x; i <= nk; i += (int)blockDim.x) {  // (entry nk: the last knot, for cell nk - 1)
         ColCell<T> c;
         c.l = i > 0 ? S.ks[ax][i - 1] : T(0);
-        c.r = S.rr[ax][i];
+        c.r = i < nk ? S.rr[ax][i] : T(0);
         cl[i] = c;
       }
-      off += (nk * (int)sizeof(ColCell<T>) + 15) & ~15;
+      off += ((nk + 1) * (int)sizeof(ColCell<T>) + 15) & ~15;
     }
   }
   __syncthreads();
   int cells_bytes = 0;
 #pragma unroll
-  for (int ax = 0; ax < ND; ++ax) cells_bytes += (a.ax[ax].nk * (int)sizeof(ColCell<T>) + 15) & ~15;
+  for (int ax = 0; ax < ND; ++ax) cells_bytes += ((a.ax[ax].nk + 1) * (int)sizeof(ColCell<T>) + 15) & ~15;
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -195,24 +209,26 @@ stencil_column_kernel(const __grid_constant__ StArgs<T, 3> a, const int ry, cons
         const int iy_last = __shfl_sync(0xffffffffu, pi[1], lead - 1);
         const int pos_last = __shfl_sync(0xffffffffu, pos, lead - 1);
         int e, ncol;
-        if (lead == 1 && pos_last < len - 1) {
+        if (pos_last >= len - 1) {
+          e = len;  // the rest of the segment
+          ncol = iy_last - iy0 + 1;
+        } else if (lead == 1) {
           // not even the second probe is inside (sparse or unsorted stretch): take one step anyway;
           // what falls outside the staged columns goes through the one-query path
           e = min(s + kColStep, len);
           ncol = min(K, nky - iy0);
         } else {
-          e = pos_last + 1;
+          e = pos_last;  // (whole rounds: the last probe inside starts the next window)
           ncol = iy_last - iy0 + 1;
         }
         // (the probes did not need the buffer; now wait until the consumers have handed it back,
-        // sleeping between polls: this warp shares its scheduler with three consumer warps)
-        if (k >= 2) {
-          while (!col_mbar_test(mbar_s + 16 + 8 * b, (unsigned)(((k >> 1) + 1) & 1))) __nanosleep(200);
-        }
+        // parked in hardware: this warp shares its scheduler with three consumer warps)
+        if (k >= 2) col_mbar_wait(mbar_s + 16 + 8 * b, (unsigned)(((k >> 1) + 1) & 1));
         const int nry = ncol + 3;
         const int nrows = 4 * nry;
         if (lane == 0) {
           HDR[b].s = s; HDR[b].e = e; HDR[b].ix0 = ix0; HDR[b].iy0 = iy0; HDR[b].ncol = ncol; HDR[b].seg = sg;
+          NEXT_ROUND[b] = 0;
           st_mbar_expect_tx(mbar_s + 8 * b, (unsigned)(nrows * row_bytes));
         }
         __syncwarp();
@@ -230,9 +246,7 @@ stencil_column_kernel(const __grid_constant__ StArgs<T, 3> a, const int ry, cons
     }
     // no more windows
     const int b = k & 1;
-    if (k >= 2) {
-      while (!col_mbar_test(mbar_s + 16 + 8 * b, (unsigned)(((k >> 1) + 1) & 1))) __nanosleep(200);
-    }
+    if (k >= 2) col_mbar_wait(mbar_s + 16 + 8 * b, (unsigned)(((k >> 1) + 1) & 1));
     if (lane == 0) {
       HDR[b].s = 0; HDR[b].e = 0;
       col_mbar_arrive(mbar_s + 8 * b);
@@ -242,68 +256,141 @@ stencil_column_kernel(const __grid_constant__ StArgs<T, 3> a, const int ry, cons
 
   // --------------------------------- consumers ----------------------------------------
   char* const xch = xch0 + warp * Cfg::XCH_BYTES;
-  T* const tq = reinterpret_cast<T*>(xch);                            // [3][64]
-  uint2* const meta = reinterpret_cast<uint2*>(xch + Cfg::TQ_BYTES);  // [64]
-  const unsigned xch_s = (unsigned)__cvta_generic_to_shared(xch) + (unsigned)(2 * lane * (int)sizeof(T));
-  const unsigned le_mask = 0xffffffffu >> (31 - lane);
+  const T* const cb = reinterpret_cast<const T*>(xch) + 2 * lane;  // the lane's two slots of axis 0
+  const unsigned cb_s = (unsigned)__cvta_generic_to_shared(xch) + (unsigned)(2 * lane * (int)sizeof(T));
   bool can_fill[ND];
   unsigned high_order = 0;  // axes whose derivative order the regular-cell taps do not cover
+  bool vec_ok = true;       // 16-byte (float: 8-byte) copies of a lane's two coordinates
 #pragma unroll
   for (int ax = 0; ax < ND; ++ax) {
     can_fill[ax] = !IPXC_WRAP(ax) && (!P.axis[ax].keep_lo || !P.axis[ax].keep_hi);
     if (!ORD0 && P.axis[ax].derivative > 1) high_order |= 1u << ax;
+    vec_ok = vec_ok && (reinterpret_cast<uintptr_t>(a.ax[ax].q) & (2 * sizeof(T) - 1)) == 0;
   }
   const int plane_bytes = ry * rs;
+  // general taps of cell i of one axis; the table pointers are formed here, behind an opaque zero,
+  // so that the compiler does not carry nine of them through the hot loop for a rare branch
+  auto general_taps = [&](int ax, int i, T t, T (&tp)[4]) {
+    int zero;
+    asm volatile("mov.u32 %0, 0;" : "=r"(zero));
+    const StLayout<ND> lay = st_layout<T, ND>(a);
+    const char* sm = smem + zero;
+    const T* ks = reinterpret_cast<const T*>(sm + lay.ks_off[ax]);
+    const T* rr = reinterpret_cast<const T*>(sm + lay.rr_off[ax]);
+    const Coef2<T>* ac = reinterpret_cast<const Coef2<T>*>(sm + lay.ac_off[ax]);
+    const Taps4<T> g = st_taps_general_inl<T>(ks, ac, i, t, t_abs(rr[i]), ORD0 ? 0 : P.axis[ax].derivative);
+    tp[0] = g.t0; tp[1] = g.t1; tp[2] = g.t2; tp[3] = g.t3;
+  };
 
-  // coordinates of up to 64 queries from position c of the segment travel global -> shared (the
-  // lane's own two slots per axis: entries 2 * lane and 2 * lane + 1 of tq[ax]) while it computes
-  auto prefetch = [&](const int64_t seg0, int c, int end) {
+  // the coordinates of the lane's two queries of the round at `pos` travel global -> shared (its
+  // own slots, entries 2 * lane and 2 * lane + 1 of each axis) while the current round is computed
+  auto prefetch = [&](const int64_t seg0, int pos) {
+    const int64_t qi = seg0 + pos + 2 * lane;
+    if (vec_ok && qi + 1 < a.nq) {
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int qi = c + 32 * k + lane;
-      if (qi < end) {
+      for (int ax = 0; ax < ND; ++ax)
+        col_cp_async<2 * (int)sizeof(T)>(cb_s + (unsigned)(ax * 64 * (int)sizeof(T)), a.ax[ax].q + qi);
+    } else {
 #pragma unroll
-        for (int ax = 0; ax < ND; ++ax)
-          col_cp_async<(int)sizeof(T)>(xch_s + (unsigned)((ax * 64 + k) * (int)sizeof(T)), a.ax[ax].q + seg0 + qi);
-      }
+      for (int k = 0; k < 2; ++k)
+        if (qi + k < a.nq) {
+#pragma unroll
+          for (int ax = 0; ax < ND; ++ax)
+            col_cp_async<(int)sizeof(T)>(cb_s + (unsigned)((ax * 64 + k) * (int)sizeof(T)), a.ax[ax].q + qi + k);
+        }
     }
   };
 
-  bool prefetched = false;
+  // The warps TAKE the rounds of a window (an atomic counter in shared memory) rather than being
+  // dealt them: the scheduler that hosts the producer warp has one consumer warp fewer than the
+  // others, and with equal shares its warps ran ahead and waited at every window.
+  auto take_round = [&](int buf) {
+    int r = 0;
+    if (lane == 0) r = atomicAdd(&NEXT_ROUND[buf], 1);
+    return __shfl_sync(0xffffffffu, r, 0);
+  };
+  int carried = -1;  // a round of the NEXT window taken (and its coordinates requested) already
   for (int k = 0;; ++k) {
     const int b = k & 1;
-    st_mbar_wait(mbar_s + 8 * b, (unsigned)((k >> 1) & 1));
+    col_mbar_wait(mbar_s + 8 * b, (unsigned)((k >> 1) & 1));
     const int4 hd = *reinterpret_cast<const int4*>(&HDR[b]);
     const int ws = hd.x, we = hd.y;
     if (ws >= we) break;
-    const int ix0 = hd.z, iy0 = hd.w, ncol = HDR[b].ncol;
-    const int64_t seg0 = ((int64_t)HDR[b].seg * gridDim.x + blockIdx.x) * seg;
-    const int sub = (we - ws + kColWarps - 1) / kColWarps;
-    int cur = min(ws + warp * sub, we);
-    const int r1 = min(cur + sub, we);
-    if (!prefetched && cur < r1) prefetch(seg0, cur, r1);
-    prefetched = false;
-    const char* const rows = rows0 + b * buf_bytes;
-    T* const outs = a.out + seg0;
-    const ColCell<T> cell_x = CELL[0][ix0];
-    const unsigned flags0 = (high_order << 6) | (((unsigned)sign_word(cell_x.r) >> 31) << 6);
+    const int nrounds = (we - ws + 63) >> 6;
+    int rnd = carried;
+    if (rnd < 0) {
+      rnd = take_round(b);
+      if (rnd < nrounds) prefetch(((int64_t)HDR[b].seg * gridDim.x + blockIdx.x) * seg, ws + 64 * rnd);
+    }
+    carried = -1;
+    int nrnd = nrounds;  // the round after rnd (taken while rnd is worked on)
 
     // One round.  FAST: the round as the hot loop runs it, free of calls (out-of-line calls in
-    // rare branches make the compiler spill around them in the loop); it gives up -- before
-    // anything is written -- if a query of the round needs the one-query path or the general
-    // taps, and the round is then redone by the other instantiation.
+    // rare branches make the compiler spill around them in the loop); it gives up -- results it
+    // has stored are stored again -- if a query of the round needs the one-query path, and the
+    // round is then redone by the other instantiation (coordinates straight from global memory).
     auto round = [&](auto fast_tag) -> bool {
       constexpr bool FAST = decltype(fast_tag)::value;
-      // ---- phase 1: two queries per lane (cur + lane, cur + 32 + lane) located ----
-      st_cp_async_wait();
-      T c[ND][2];
+      // (the window's constants are read from shared memory every round: registers are what the
+      // contraction below is short of)
+      // (likewise the cell tables' addresses: re-formed behind an opaque zero instead of carried --
+      // and spilled -- through the loop)
+      const ColCell<T>* CELL[ND];
+      {
+        int zero;
+        asm volatile("mov.u32 %0, 0;" : "=r"(zero));
+        int off = st_layout<T, ND>(a).total + zero;
 #pragma unroll
-      for (int ax = 0; ax < ND; ++ax) col_lds_pair(tq + ax * 64 + 2 * lane, c[ax][0], c[ax][1]);
-      unsigned key[2], flg[2];  // flg: bits 0-5 fill, bits 6-8 axes that need the general taps
+        for (int ax = 0; ax < ND; ++ax) {
+          CELL[ax] = reinterpret_cast<const ColCell<T>*>(smem + off);
+          off += ((a.ax[ax].nk + 1) * (int)sizeof(ColCell<T>) + 15) & ~15;
+        }
+      }
+      const int4 hw = *reinterpret_cast<const int4*>(&HDR[b]);
+      const int ws = hw.x, we = hw.y, ix0 = hw.z, iy0 = hw.w, ncol = HDR[b].ncol;
+      const int64_t seg0 = ((int64_t)HDR[b].seg * gridDim.x + blockIdx.x) * seg;
+      const char* const rows = rows0 + b * buf_bytes;
+      T* const outs = a.out + seg0;
+      const ColCell<T> cell_x = CELL[0][ix0];
+      const T cell_hx = CELL[0][ix0 + 1].l;
+      const unsigned flags0 = (high_order << 6) | (((unsigned)sign_word(cell_x.r) >> 31) << 6);
+      const int pos = ws + 64 * rnd;
+      const int qa = pos + 2 * lane;  // the lane's queries: qa and qa + 1 (of the segment)
+      T c[ND][2];
+      if constexpr (FAST) {
+        st_cp_async_wait();
+#pragma unroll
+        for (int ax = 0; ax < ND; ++ax) col_lds_pair(cb + ax * 64, c[ax][0], c[ax][1]);
+        // (the lane's own slots, read above: the next round's coordinates can follow at once)
+        nrnd = take_round(b);
+        if (nrnd < nrounds) {
+          prefetch(seg0, ws + 64 * nrnd);
+        } else {
+          // nothing left in this window: start on the next one if its header is already there
+          const int nb = b ^ 1;
+          if (col_mbar_test(mbar_s + 8 * nb, (unsigned)(((k + 1) >> 1) & 1))) {
+            const int ns = HDR[nb].s, ne = HDR[nb].e;
+            if (ns < ne) {
+              carried = take_round(nb);
+              if (ns + 64 * carried < ne)
+                prefetch(((int64_t)HDR[nb].seg * gridDim.x + blockIdx.x) * seg, ns + 64 * carried);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+          for (int ax = 0; ax < ND; ++ax) c[ax][kk] = qa + kk < we ? a.ax[ax].q[seg0 + qa + kk] : T(0);
+      }
+      // ---- phase 1: both queries located ----
+      unsigned flg[2];  // bits 0-5 fill, bits 6-8 axes that need the general taps
+      bool slow[2];
+      int iy[2], iz[2];
       T tt[2][ND];
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk) {
-        bool slow = false;
+        bool sl = false;
         unsigned fl = flags0;
         int ii[ND];
 #pragma unroll
@@ -313,7 +400,7 @@ stencil_column_kernel(const __grid_constant__ StArgs<T, 3> a, const int ry, cons
           if (IPXC_WRAP(ax)) {
             bool wrap_bad;
             v = wrap_one_period(v, T(fabs(P.axis[ax].period)), wrap_bad);
-            slow = slow || wrap_bad;
+            sl = sl || wrap_bad;
           }
           // first axis: every cell of the window is ix0 (anything else fails the test below);
           // the others: guess from the uniform spacing
@@ -324,146 +411,128 @@ stencil_column_kernel(const __grid_constant__ StArgs<T, 3> a, const int ry, cons
           if (ax > 0) fl |= irregular << (6 + ax);
           if (!col_inside(t) || irregular) {
             // near a knot, outside the knots, NaN, or a cell that may have zero width: the exact test
-            const T h = S.ks[ax][i];
-            if (!((v >= cl.l || i == 1) && (v < h || i == nk - 1))) slow = true;
+            const T h = ax == 0 ? cell_hx : CELL[ax][i + 1].l;
+            if (!((v >= cl.l || i == 1) && (v < h || i == nk - 1))) sl = true;
             if (can_fill[ax]) fl |= st_fill_bits(P.axis[ax], AXC[ax], i, nk, v) << (2 * ax);
           }
           tt[kk][ax] = t;
           ii[ax] = i;
         }
-        slow = slow || (unsigned)(ii[1] - iy0) >= (unsigned)ncol;
-        const bool valid = cur + 32 * kk + lane < r1;
-        key[kk] = valid ? (((unsigned)ii[1] << 10) | (unsigned)ii[2] | (slow ? 1u << 30 : 0u)) : 0xffffffffu;
+        sl = sl || (unsigned)(ii[1] - iy0) >= (unsigned)ncol;
+        slow[kk] = sl && qa + kk < we;
         flg[kk] = fl;
+        iy[kk] = ii[1];
+        iz[kk] = ii[2];
       }
       if constexpr (FAST) {
-        const bool cold = (key[0] != 0xffffffffu && (((key[0] >> 30) & 1u) || (flg[0] & 0x1c0u))) ||
-                          (key[1] != 0xffffffffu && (((key[1] >> 30) & 1u) || (flg[1] & 0x1c0u)));
-        if (__any_sync(0xffffffffu, cold)) return false;  // (the coordinates are still in the buffer)
+        if (__any_sync(0xffffffffu, slow[0] || slow[1])) return false;
       }
-      __syncwarp();  // everybody holds its coordinates: the buffer now takes the exchange
-      // ---- re-pair: runs of equal keys; positions 2m, 2m+1 of a run share a lane ----
-      const unsigned pk0 = __shfl_up_sync(0xffffffffu, key[0], 1);
-      const unsigned pk1 = __shfl_up_sync(0xffffffffu, key[1], 1);
-      const unsigned k31 = __shfl_sync(0xffffffffu, key[0], 31);
-      const bool s0 = lane == 0 || key[0] != pk0;
-      const bool s1 = key[1] != (lane == 0 ? k31 : pk1);
-      const unsigned mlo = __ballot_sync(0xffffffffu, s0), mhi = __ballot_sync(0xffffffffu, s1);
-      const int p0 = lane - (31 - __clz(mlo & le_mask));
-      const unsigned mh = mhi & le_mask;
-      const int p1 = 32 + lane - (mh ? 63 - __clz(mh) : 31 - __clz(mlo));
-      const bool v0 = key[0] != 0xffffffffu, v1 = key[1] != 0xffffffffu;
-      const unsigned olo = __ballot_sync(0xffffffffu, v0 && !(p0 & 1));
-      const unsigned ohi = __ballot_sync(0xffffffffu, v1 && !(p1 & 1));
-      const int nlo = __popc(olo);
-      const int slot0 = __popc(olo & le_mask) - 1;
-      const int slot1 = nlo + __popc(ohi & le_mask) - 1;
-      const bool take0 = v0, take1 = v1 && slot1 < 32;  // (slot0 <= 31 always)
-      // queries taken: all valid ones of the first half, and those of the second up to slot 31
-      const int taken = __popc(__ballot_sync(0xffffffffu, v0)) + __popc(__ballot_sync(0xffffffffu, take1));
-      const int nslots = min(32, nlo + __popc(ohi));
-      // the entry after mine continues my run (only read for first halves)
-      const bool cont0 = lane < 31 ? !((mlo >> (lane + 1)) & 1u) : !(mhi & 1u);
-      const bool cont1 = lane < 31 && !((mhi >> (lane + 1)) & 1u);
-      if (take0) {
-        const int e = 2 * slot0 + (p0 & 1);
-#pragma unroll
-        for (int ax = 0; ax < ND; ++ax) tq[ax * 64 + e] = tt[0][ax];
-        meta[e] = make_uint2(key[0] | (cont0 ? 1u << 31 : 0u), (unsigned)lane | (flg[0] << 8));
+      const bool val0 = qa < we, val1 = qa + 1 < we;
+      // the second query rides with the first if it sits in its cell or the next one up the last axis
+      const int dz = iz[1] - iz[0];
+      const bool ride = val1 && !slow[0] && !slow[1] && iy[1] == iy[0] && (dz == 0 || dz == 1);
+      // second queries that do not ride (other column, more than a cell away: rare in a dense
+      // cell-sorted stream) take a second pass of the same code -- in the cold instantiation only
+      bool pend = val1 && !slow[1] && !ride;
+      if constexpr (FAST) {
+        if (__any_sync(0xffffffffu, pend)) return false;
       }
-      if (take1) {
-        const int e = 2 * slot1 + (p1 & 1);
+      bool nan_seen = false;
+      // the pass's first query (no run-time indexing: the arrays stay in registers)
+      T at[ND];
 #pragma unroll
-        for (int ax = 0; ax < ND; ++ax) tq[ax * 64 + e] = tt[1][ax];
-        meta[e] = make_uint2(key[1] | (cont1 ? 1u << 31 : 0u), (unsigned)(32 + lane) | (flg[1] << 8));
-      }
-      __syncwarp();
-      // ---- phase 2: the lane's pair ----
-      const uint4 mm = *reinterpret_cast<const uint4*>(meta + 2 * lane);
-      T ta[ND], tb[ND];
+      for (int ax = 0; ax < ND; ++ax) at[ax] = tt[0][ax];
+      unsigned aflg = flg[0];
+      int cy = iy[0], cz = iz[0], ka = 0;
+      bool act_a = val0 && !slow[0], act_b = ride;
+#pragma unroll 1
+      for (int pass = 0; pass < (FAST ? 1 : 2); ++pass) {
+        bool nan_a = false, nan_b = false;
+        if (act_a) {
+          T TA[ND][4], TBX[4], TBY[4], TBZ[5];
+          const unsigned gen_a = (aflg >> 6) & 7u, gen_b = (flg[1] >> 6) & 7u;
 #pragma unroll
-      for (int ax = 0; ax < ND; ++ax) col_lds_pair(tq + ax * 64 + 2 * lane, ta[ax], tb[ax]);
-      __syncwarp();  // exchange read: the buffer takes the next round's coordinates
-      const int nxt = cur + taken;
-      if (nxt < r1) {
-        prefetch(seg0, nxt, r1);
-      } else {
-        // last round of this window: start on the next one if its header is already there
-        const int nb = b ^ 1;
-        if (col_mbar_test(mbar_s + 8 * nb, (unsigned)(((k + 1) >> 1) & 1))) {
-          const int ns = HDR[nb].s, ne = HDR[nb].e;
-          if (ns < ne) {
-            const int nsub = (ne - ns + kColWarps - 1) / kColWarps;
-            const int n0 = min(ns + warp * nsub, ne);
-            const int n1 = min(n0 + nsub, ne);
-            if (n0 < n1) {
-              prefetch(((int64_t)HDR[nb].seg * gridDim.x + blockIdx.x) * seg, n0, n1);
-              prefetched = true;
+          for (int ax = 0; ax < ND; ++ax) {
+            const int i = ax == 0 ? ix0 : (ax == 1 ? cy : cz);
+            if ((gen_a >> ax) & 1u) {
+              general_taps(ax, i, at[ax], TA[ax]);
+            } else {
+              col_taps<T, ORD0>(at[ax], ORD0 ? T(0) : t_abs(CELL[ax][i].r), P.axis[ax].derivative, TA[ax]);
             }
           }
-        }
-      }
-      // the slow queries of this round (rare), by the lane that located them
-      if constexpr (!FAST) {
-        const bool slow0 = take0 && ((key[0] >> 30) & 1u), slow1 = take1 && ((key[1] >> 30) & 1u);
-        if (slow0 || slow1) {
-          if (slow0) st_redo<T, ND, ORD0>(&a, &P, smem, AXC, seg0 + cur + lane, 1u);
-          if (slow1) st_redo<T, ND, ORD0>(&a, &P, smem, AXC, seg0 + cur + 32 + lane, 1u);
-        }
-      }
-      const bool act_a = lane < nslots && !((mm.x >> 30) & 1u);
-      const bool act_b = act_a && (mm.x >> 31) != 0u;
-      if (act_a) {
-        const int ix = ix0, iy = (mm.x >> 10) & 1023, iz = mm.x & 1023;
-        T TA[ND][4], TB[ND][4];
-        const unsigned gen = (mm.y >> 14) & 7u;  // (the pair shares the cell, hence these flags)
+          {
+            // the rider's taps: its own cell along the last axis (iz[1]), the pair's on the others
+            T tb[ND][4];
 #pragma unroll
-        for (int ax = 0; ax < ND; ++ax) {
-          const int i = ax == 0 ? ix : (ax == 1 ? iy : iz);
-          if (!FAST && ((gen >> ax) & 1u)) {
-            const T rabs = t_abs(S.rr[ax][i]);
-            const int order = ORD0 ? 0 : P.axis[ax].derivative;
-            const Taps4<T> ga = st_taps_general_t<T>(S.ks[ax], S.ac[ax], i, ta[ax], rabs, order);
-            const Taps4<T> gb = st_taps_general_t<T>(S.ks[ax], S.ac[ax], i, tb[ax], rabs, order);
-            TA[ax][0] = ga.t0; TA[ax][1] = ga.t1; TA[ax][2] = ga.t2; TA[ax][3] = ga.t3;
-            TB[ax][0] = gb.t0; TB[ax][1] = gb.t1; TB[ax][2] = gb.t2; TB[ax][3] = gb.t3;
-          } else {
-            const T r = ORD0 ? T(0) : S.rr[ax][i];
-            col_taps<T, ORD0>(ta[ax], r, P.axis[ax].derivative, TA[ax]);
-            col_taps<T, ORD0>(tb[ax], r, P.axis[ax].derivative, TB[ax]);
+            for (int ax = 0; ax < ND; ++ax) {
+              const int i = ax == 0 ? ix0 : (ax == 1 ? cy : iz[1]);
+              if (act_b && ((gen_b >> ax) & 1u)) {
+                general_taps(ax, i, tt[1][ax], tb[ax]);
+              } else {
+                col_taps<T, ORD0>(tt[1][ax], ORD0 ? T(0) : t_abs(CELL[ax][i].r), P.axis[ax].derivative, tb[ax]);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { TBX[j] = tb[0][j]; TBY[j] = tb[1][j]; }
+            const bool same = dz == 0;
+            TBZ[0] = same ? tb[2][0] : T(0);
+            TBZ[1] = same ? tb[2][1] : tb[2][0];
+            TBZ[2] = same ? tb[2][2] : tb[2][1];
+            TBZ[3] = same ? tb[2][3] : tb[2][2];
+            TBZ[4] = same ? T(0) : tb[2][3];
           }
-        }
-        const char* base = rows + (iy - iy0) * rs + (iz - 1) * (int)sizeof(T);
-        T acc_a = T(0), acc_b = T(0);
+          const char* base = rows + (cy - iy0) * rs + (cz - 1) * (int)sizeof(T);
+          T acc_a = T(0), acc_b = T(0);
 #pragma unroll
-        for (int aa = 0; aa < 4; ++aa) {
-          T sya = T(0), syb = T(0);
+          for (int aa = 0; aa < 4; ++aa) {
+            T sya = T(0), syb = T(0);
 #pragma unroll
-          for (int bb = 0; bb < 4; ++bb) {
-            const T* p = reinterpret_cast<const T*>(base + bb * rs);
-            const T f0 = p[0], f1 = p[1], f2 = p[2], f3 = p[3];
-            T ra = TA[2][0] * f0, rb = TB[2][0] * f0;
-            ra = fma(TA[2][1], f1, ra); rb = fma(TB[2][1], f1, rb);
-            ra = fma(TA[2][2], f2, ra); rb = fma(TB[2][2], f2, rb);
-            ra = fma(TA[2][3], f3, ra); rb = fma(TB[2][3], f3, rb);
-            sya = fma(TA[1][bb], ra, sya);
-            syb = fma(TB[1][bb], rb, syb);
+            for (int bb = 0; bb < 4; ++bb) {
+              const T* p = reinterpret_cast<const T*>(base + bb * rs);
+              const T f0 = p[0], f1 = p[1], f2 = p[2], f3 = p[3], f4 = p[4];
+              T ra = TA[2][0] * f0, rb = TBZ[0] * f0;
+              ra = fma(TA[2][1], f1, ra); rb = fma(TBZ[1], f1, rb);
+              ra = fma(TA[2][2], f2, ra); rb = fma(TBZ[2], f2, rb);
+              ra = fma(TA[2][3], f3, ra); rb = fma(TBZ[3], f3, rb);
+              rb = fma(TBZ[4], f4, rb);
+              sya = fma(TA[1][bb], ra, sya);
+              syb = fma(TBY[bb], rb, syb);
+            }
+            acc_a = fma(TA[0][aa], sya, acc_a);
+            acc_b = fma(TBX[aa], syb, acc_b);
+            base += plane_bytes;
           }
-          acc_a = fma(TA[0][aa], sya, acc_a);
-          acc_b = fma(TB[0][aa], syb, acc_b);
-          base += plane_bytes;
+          // a NaN may be a non-finite table entry under the zero tap: the one-query path decides
+          nan_a = acc_a != acc_a;
+          nan_b = act_b && acc_b != acc_b;
+          __stcs(outs + qa + ka, st_apply_fill<T, ND>(P, aflg & 63u, acc_a));
+          if (act_b) __stcs(outs + qa + 1, st_apply_fill<T, ND>(P, flg[1] & 63u, acc_b));
         }
-        const unsigned fa = (mm.y >> 8) & 63u, fb = (mm.w >> 8) & 63u;
-        __stcs(outs + (cur + (int)(mm.y & 63u)), st_apply_fill<T, ND>(P, fa, acc_a));
-        if (act_b) __stcs(outs + (cur + (int)(mm.w & 63u)), st_apply_fill<T, ND>(P, fb, acc_b));
+        nan_seen = nan_seen || nan_a || nan_b;
+        if constexpr (!FAST) {
+          if (nan_a) { if (ka == 0) slow[0] = true; else slow[1] = true; }
+          if (nan_b) slow[1] = true;
+          if (!__any_sync(0xffffffffu, pend)) break;
+          // second pass: the second queries that did not ride, alone
+#pragma unroll
+          for (int ax = 0; ax < ND; ++ax) at[ax] = tt[1][ax];
+          aflg = flg[1]; cy = iy[1]; cz = iz[1]; ka = 1;
+          act_a = pend; act_b = false; pend = false;
+        }
       }
-      cur = nxt;
+      if constexpr (FAST) {
+        if (__any_sync(0xffffffffu, nan_seen)) return false;
+      } else {
+        if (slow[0] || slow[1]) {
+          if (slow[0]) st_redo<T, ND, ORD0>(&a, &P, smem, AXC, seg0 + qa, 1u);
+          if (slow[1]) st_redo<T, ND, ORD0>(&a, &P, smem, AXC, seg0 + qa + 1, 1u);
+        }
+      }
       return true;
     };
-    while (cur < r1) {
-      while (cur < r1 && round(std::true_type{})) {
-      }
-      if (cur < r1) round(std::false_type{});
+    while (rnd < nrounds) {
+      if (!round(std::true_type{})) round(std::false_type{});
+      rnd = nrnd;
     }
     __syncwarp();
     if (lane == 0) col_mbar_arrive(mbar_s + 16 + 8 * b);
@@ -471,24 +540,37 @@ stencil_column_kernel(const __grid_constant__ StArgs<T, 3> a, const int ry, cons
 #undef IPXC_WRAP
 }
 
-// launch; IPX_EUNSUPPORTED when the shape does not apply (the caller uses another one)
-template <typename T>
-static int st_launch_column(const StArgs<T, 3>& a, const StDevice& d, cudaStream_t s) {
+// shared-memory plan of a launch; false when the shape does not apply (long knot vectors or rows,
+// interval indices requested)
+struct ColPlan {
+  long long ry, rs;
+  size_t smem;
+};
+template <typename T> static bool st_column_plan(const StArgs<T, 3>& a, const StDevice& d, ColPlan& pl) {
   const StLayout<3> lay = st_layout<T, 3>(a);
   long long cells = 0;
   for (int ax = 0; ax < 3; ++ax) {
-    if (a.ax[ax].nk > 1023) return IPX_EUNSUPPORTED;  // cell indices travel in 10 bits each
-    cells += ((long long)a.ax[ax].nk * (long long)sizeof(ColCell<T>) + 15) & ~15ll;
+    if (a.ax[ax].nk > 1023) return false;  // cell indices travel in 10 bits each
+    cells += ((long long)(a.ax[ax].nk + 1) * (long long)sizeof(ColCell<T>) + 15) & ~15ll;
   }
-  if (a.idx_out != nullptr) return IPX_EUNSUPPORTED;
-  const long long row_bytes = (long long)a.pitch * (long long)sizeof(T);
-  const long long rs = row_bytes;  // row stride in shared memory
+  if (a.idx_out != nullptr) return false;
+  pl.rs = (long long)a.pitch * (long long)sizeof(T);  // row stride in shared memory = row bytes
   const long long fixed = (long long)lay.total + cells + (long long)kColWarps * ColCfg<T>::XCH_BYTES;
   const long long room = (long long)d.smem_optin - 2048 - fixed;
-  long long ry = room / (2 * 4 * rs);
-  if (ry > 32) ry = 32;
-  if (ry < 5) return IPX_EUNSUPPORTED;  // fewer than two columns per window
-  const size_t smem = (size_t)(fixed + 2 * 4 * ry * rs);
+  pl.ry = room / (2 * 4 * pl.rs);
+  if (pl.ry > 32) pl.ry = 32;
+  if (pl.ry < 5) return false;  // fewer than two columns per window
+  pl.smem = (size_t)(fixed + 2 * 4 * pl.ry * pl.rs);
+  return true;
+}
+
+// launch; IPX_EUNSUPPORTED when the shape does not apply (the caller uses another one)
+template <typename T>
+static int st_launch_column(const StArgs<T, 3>& a, const StDevice& d, cudaStream_t s) {
+  ColPlan pl;
+  if (!st_column_plan<T>(a, d, pl)) return IPX_EUNSUPPORTED;
+  const long long ry = pl.ry, rs = pl.rs;
+  const size_t smem = pl.smem;
   bool ord0 = a.dp == nullptr;
   for (int ax = 0; ax < 3 && ord0; ++ax) ord0 = a.hp.axis[ax].derivative <= 0;
   int mask = 0;
