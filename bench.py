@@ -424,6 +424,20 @@ def run_ours(args):
     ms_fun, nl = timed(lambda: ipx.interp3d(*sq, xk, yk, zk, f, "cubic", deriv, extrap, period),
                        max(3, steps // 2), 3)
     launches += nl
+    # the evaluation from f alone on the same cell-sorted queries (halo table, 1/8 of the records'
+    # bytes; in 3-D the column shape: rows staged by cp.async.bulk): what a caller without the
+    # packed records gets
+    from interpax_b200 import _lib as _L
+    from interpax_b200 import api as _api
+    ms_from_f = None
+    if getattr(ip, "_halo", None) is not None:
+        old_hint = _api.stencil_hint
+        _api.stencil_hint = _L.IPX_STENCIL_COLUMN if args.config == "c4" else _L.IPX_STENCIL_SPARSE
+        try:
+            ms_from_f, nl = timed(lambda: ip(*sq, *deriv), max(3, steps // 2), 3)
+            launches += nl
+        finally:
+            _api.stencil_hint = old_hint
 
     # ---- spot parity of what was just timed (first 4096 sorted queries), rank 0 ----
     parity = None
@@ -575,6 +589,12 @@ def run_ours(args):
                             "query_order": "cell-sorted",
                             "note": "interp3d(xq, yq, zq, x, y, z, f, 'cubic', ...): tables rebuilt from f inside "
                                     "every call (the reference recomputes its 7 slope tables per call)"},
+        "evaluation_from_f": None if ms_from_f is None else {
+            "value": total_q / (ms_from_f * 1e-3), "ms_per_step": ms_from_f, "query_order": "cell-sorted",
+            "roofline_frac": bytes_launch / (ms_from_f * 1e-3) / 1e9 / peak,
+            "note": "same call with the kernel shape forced to the evaluation straight from f (halo table: "
+                    "1/8 of the records' bytes, no slope tables); C4: ipx::stencil_column_kernel, table rows "
+                    "staged in shared memory by cp.async.bulk + mbarrier"},
         "e2e": e2e,
         "gpu_launches": launches,
         "clocks": sampler.summary(),

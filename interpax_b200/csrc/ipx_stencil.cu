@@ -1276,11 +1276,12 @@ static int launch_stencil(const T* const* q, int64_t nq, const T* const* knots, 
   // (the tile kernel on the records overtakes the sparse shape between three and six queries per
   // cell: 256^3 f64, 5e7 queries 1.73 vs 1.44 ms, 1e8 queries 1.86 vs 2.83 ms)
   const bool rec_quads = records != nullptr && ND == 3 && dense_ok && (double)nq >= 4.0 * cells;
-  // (without records, dense cell-sorted 3-D streams go to the column shape: 2.2 vs 2.8 ms)
+  // (without records, dense cell-sorted 3-D streams go to the column shape: 256^3 f64, 1e8 queries
+  // 2.07 vs 2.79 ms; at 5e7 queries, three per cell, the sparse shape is still ahead, 1.46 vs 1.76)
   bool col_quads = false;
   if constexpr (ND == 3) {
     ColPlan pl;
-    col_quads = !rec_quads && dense_ok && (double)nq >= 4.0 * cells && st_column_plan<T>(a, d, pl);
+    col_quads = !rec_quads && dense_ok && (double)nq >= 4.5 * cells && st_column_plan<T>(a, d, pl);
   }
   if (!dense && !rec_random && !rec_quads && !col_quads) return st_launch_q<T, ND, false, 4>(a, d, s);  // one candidate: no probe
   stencil_probe_kernel<T, ND, IPX_STENCIL_TAPS><<<1, 256, 0, s>>>(a, workspace);
