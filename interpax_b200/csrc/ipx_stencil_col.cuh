@@ -86,6 +86,16 @@ __device__ __forceinline__ void col_mbar_wait(unsigned mbar_s, unsigned phase) {
       "IPX_COL_DONE:\n"
       "}\n" ::"r"(mbar_s), "r"(phase), "r"(0x989680u) : "memory");
 }
+// "buffer b is free again": a named barrier (ids 1, 2) per row buffer.  Consumer warps arrive when
+// they are done with a window, the producer warp syncs before it refills the buffer -- blocked in
+// hardware, where polling an mbarrier cost 6 % of the kernel's instructions on the scheduler the
+// producer shares with three consumers (try_wait's suspend hint parks a warp for ~20 ns at a time).
+__device__ __forceinline__ void col_free_arrive(int b) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(1 + b), "r"((kColWarps + 1) * 32) : "memory");
+}
+__device__ __forceinline__ void col_free_wait(int b) {
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + b), "r"((kColWarps + 1) * 32) : "memory");
+}
 __device__ __forceinline__ void col_mbar_arrive(unsigned mbar_s) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(mbar_s) : "memory");
 }
@@ -137,7 +147,7 @@ stencil_column_kernel(const __grid_constant__ StArgs<T, 3> a, const int ry, cons
   __shared__ StAxC<T> AXC[ND];
   __shared__ ipx_params params_s;
   __shared__ __align__(16) ColHdr HDR[2];
-  __shared__ __align__(8) unsigned long long MBAR[4];  // full[0], full[1], free[0], free[1]
+  __shared__ __align__(8) unsigned long long MBAR[2];  // full[0], full[1] (rows of a window have landed)
   __shared__ int NEXT_ROUND[2];  // per row buffer: the next round of its window nobody has taken yet
   if (a.flag != nullptr && ((a.accept >> (*a.flag & 31)) & 1u) == 0) return;
   if (DEVP && threadIdx.x == 32) params_s = *a.dp;
@@ -146,8 +156,6 @@ stencil_column_kernel(const __grid_constant__ StArgs<T, 3> a, const int ry, cons
   if (threadIdx.x == 0) {
     st_mbar_init(mbar_s, 1);
     st_mbar_init(mbar_s + 8, 1);
-    st_mbar_init(mbar_s + 16, kColWarps);
-    st_mbar_init(mbar_s + 24, kColWarps);
   }
   StShared<T, ND> S;
   st_stage<T, ND>(a, smem, AXC, S);  // (ends with a barrier: the mbarriers are initialised too)
@@ -223,7 +231,7 @@ stencil_column_kernel(const __grid_constant__ StArgs<T, 3> a, const int ry, cons
         }
         // (the probes did not need the buffer; now wait until the consumers have handed it back,
         // parked in hardware: this warp shares its scheduler with three consumer warps)
-        if (k >= 2) col_mbar_wait(mbar_s + 16 + 8 * b, (unsigned)(((k >> 1) + 1) & 1));
+        if (k >= 2) col_free_wait(b);
         const int nry = ncol + 3;
         const int nrows = 4 * nry;
         if (lane == 0) {
@@ -246,7 +254,7 @@ stencil_column_kernel(const __grid_constant__ StArgs<T, 3> a, const int ry, cons
     }
     // no more windows
     const int b = k & 1;
-    if (k >= 2) col_mbar_wait(mbar_s + 16 + 8 * b, (unsigned)(((k >> 1) + 1) & 1));
+    if (k >= 2) col_free_wait(b);
     if (lane == 0) {
       HDR[b].s = 0; HDR[b].e = 0;
       col_mbar_arrive(mbar_s + 8 * b);
@@ -268,6 +276,7 @@ stencil_column_kernel(const __grid_constant__ StArgs<T, 3> a, const int ry, cons
     vec_ok = vec_ok && (reinterpret_cast<uintptr_t>(a.ax[ax].q) & (2 * sizeof(T) - 1)) == 0;
   }
   const int plane_bytes = ry * rs;
+  const bool out_vec_ok = (reinterpret_cast<uintptr_t>(a.out) & (2 * sizeof(T) - 1)) == 0;
   // general taps of cell i of one axis; the table pointers are formed here, behind an opaque zero,
   // so that the compiler does not carry nine of them through the hot loop for a rare branch
   auto general_taps = [&](int ax, int i, T t, T (&tp)[4]) {
@@ -505,8 +514,23 @@ stencil_column_kernel(const __grid_constant__ StArgs<T, 3> a, const int ry, cons
           // a NaN may be a non-finite table entry under the zero tap: the one-query path decides
           nan_a = acc_a != acc_a;
           nan_b = act_b && acc_b != acc_b;
-          __stcs(outs + qa + ka, st_apply_fill<T, ND>(P, aflg & 63u, acc_a));
-          if (act_b) __stcs(outs + qa + 1, st_apply_fill<T, ND>(P, flg[1] & 63u, acc_b));
+          const T res_a = st_apply_fill<T, ND>(P, aflg & 63u, acc_a);
+          if (act_b) {
+            // (qa is even and the segments start at multiples of 64: the pair is aligned if `out` is)
+            const T res_b = st_apply_fill<T, ND>(P, flg[1] & 63u, acc_b);
+            if (out_vec_ok) {
+              if constexpr (sizeof(T) == 8) {
+                __stcs(reinterpret_cast<double2*>(outs + qa), make_double2(res_a, res_b));
+              } else {
+                __stcs(reinterpret_cast<float2*>(outs + qa), make_float2(res_a, res_b));
+              }
+            } else {
+              __stcs(outs + qa, res_a);
+              __stcs(outs + qa + 1, res_b);
+            }
+          } else {
+            __stcs(outs + qa + ka, res_a);
+          }
         }
         nan_seen = nan_seen || nan_a || nan_b;
         if constexpr (!FAST) {
@@ -535,7 +559,7 @@ stencil_column_kernel(const __grid_constant__ StArgs<T, 3> a, const int ry, cons
       rnd = nrnd;
     }
     __syncwarp();
-    if (lane == 0) col_mbar_arrive(mbar_s + 16 + 8 * b);
+    col_free_arrive(b);
   }
 #undef IPXC_WRAP
 }

@@ -246,3 +246,110 @@ def test_stencil_full_size_c4_dense_vs_sparse():
     want = O.Interpolator3D(x.cpu().numpy(), x.cpu().numpy(), z.cpu().numpy(), f.cpu().numpy(), "cubic",
                             extrap, period)(xq[sel].cpu().numpy(), yq[sel].cpu().numpy(), zq[sel].cpu().numpy())
     assert_parity(dense[sel].cpu().numpy(), want)
+
+
+def test_stencil_abi_device_params_every_shape_and_graph_capture():
+    """ipx_eval_stencil_f64 through the C ABI with the traced operands (derivative orders, fills,
+    periods) in DEVICE memory -- what an XLA custom call hands over -- for every kernel shape,
+    against the same call with host operands, bit for bit; and the automatic choice (probe +
+    column / sparse candidates, no records) captured in a CUDA graph."""
+    import ctypes as C
+
+    lib = L.load()
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(4)
+    n = 24
+    P = 2 * np.pi
+    x = torch.arange(n, dtype=torch.float64, device=dev) * (P / n)
+    z = torch.linspace(0, 1, n, dtype=torch.float64, device=dev)
+    f = torch.randn((n, n, n), dtype=torch.float64, device=dev, generator=g)
+    nq = 1 << 17
+    xq = (torch.rand(nq, dtype=torch.float64, device=dev, generator=g) * 3 - 1) * P
+    yq = (torch.rand(nq, dtype=torch.float64, device=dev, generator=g) * 3 - 1) * P
+    zq = torch.rand(nq, dtype=torch.float64, device=dev, generator=g) * 1.1 - 0.05
+    h = P / n
+    key = ((xq.remainder(P) / h).floor().long() * n + (yq.remainder(P) / h).floor().long()) * (n + 2) \
+        + (zq.clamp(0, 1) * (n - 1)).floor().long()
+    order = torch.argsort(key)
+    qs = [xq[order].contiguous(), yq[order].contiguous(), zq[order].contiguous()]
+    ip = ipx.Interpolator3D(x, x, z, f, "cubic", ((True, True), (True, True), (True, 0.0)), (P, P, None))
+    assert ip._halo is not None
+    kuse = [ip._periodic(0, P)[0], ip._periodic(1, P)[0], z]
+    mask = L.IPX_PERIODIC(0) | L.IPX_PERIODIC(1)
+    ns = (C.c_int32 * 3)(n, n, n)
+    fn = lib.ipx_eval_stencil_f64
+    stream = torch.cuda.current_stream().cuda_stream
+    ws = torch.zeros(4, dtype=torch.int32, device=dev)
+    for deriv in ((0, 0, 0), (1, 0, 2)):
+        p = api._make_params(3, deriv, api._parse_extrap(ip.extrap, 3), (P, P, None))
+        pbytes = torch.frombuffer(bytearray(bytes(p)), dtype=torch.uint8).to(dev)
+        pdev = C.cast(C.c_void_p(pbytes.data_ptr()), C.POINTER(L.Params))
+        want = O.Interpolator3D(x.cpu().numpy(), x.cpu().numpy(), z.cpu().numpy(), f.cpu().numpy(), "cubic",
+                                ip.extrap, ip.period)(*[q[:4096].cpu().numpy() for q in qs], *deriv)
+        ref = None
+        for hint_code in (L.IPX_STENCIL_SPARSE, L.IPX_STENCIL_DENSE, L.IPX_STENCIL_COLUMN, L.IPX_STENCIL_AUTO):
+            outs = []
+            for params, pod in ((C.byref(p), 0), (pdev, 1)):
+                out = torch.full((nq,), -3.0, dtype=torch.float64, device=dev)
+                rc = fn(3, api._ptr_array(qs), nq, api._ptr_array(kuse), api._ptr_array([x, x, z]), ns,
+                        ip._halo.data_ptr(), None, L.IPX_SLOPE_CUBIC, 0.0, mask, params, pod, out.data_ptr(), None,
+                        hint_code, ws.data_ptr() if hint_code == L.IPX_STENCIL_AUTO else None, stream)
+                assert rc == L.IPX_OK
+                outs.append(out)
+            torch.cuda.synchronize()
+            assert torch.equal(outs[0], outs[1]), (deriv, hint_code)
+            if ref is None:
+                ref = outs[0]
+                assert_parity(ref[:4096].cpu().numpy(), want)
+            assert torch.equal(outs[0], ref), (deriv, hint_code)
+    # the automatic choice as a CUDA graph (the probe, both candidates and their skip logic captured)
+    p = api._make_params(3, (0, 0, 0), api._parse_extrap(ip.extrap, 3), (P, P, None))
+    out_g = torch.zeros(nq, dtype=torch.float64, device=dev)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    keep = (api._ptr_array(qs), api._ptr_array(kuse), api._ptr_array([x, x, z]))
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(graph, stream=s):
+            rc = fn(3, keep[0], nq, keep[1], keep[2], ns, ip._halo.data_ptr(), None, L.IPX_SLOPE_CUBIC, 0.0, mask,
+                    C.byref(p), 0, out_g.data_ptr(), None, L.IPX_STENCIL_AUTO, ws.data_ptr(),
+                    torch.cuda.current_stream().cuda_stream)
+            assert rc == L.IPX_OK
+    graph.replay()
+    torch.cuda.synchronize()
+    with hint(L.IPX_STENCIL_SPARSE):
+        assert torch.equal(out_g, ip(*qs))
+
+
+def test_small_calls_reuse_a_call_plan():
+    """Interpolator*.__call__ with small device-resident query sets goes through a per-instance
+    call plan after the first call (api._fast_call): same results as the general path for every
+    derivative order, N-D query shapes, `out=`, and anything the plan does not cover (other dtype,
+    NumPy queries, non-contiguous tensors) still takes the general path."""
+    dev = torch.device("cuda")
+    rng = np.random.default_rng(3)
+    xk = np.sort(rng.uniform(0, 1, 30))
+    yk = np.linspace(-1, 1, 17)
+    f = rng.normal(size=(30, 17))
+    ip = ipx.Interpolator2D(torch.from_numpy(xk).to(dev), torch.from_numpy(yk).to(dev), torch.from_numpy(f).to(dev),
+                            "cubic", extrap=(False, True))
+    xq = torch.from_numpy(rng.uniform(-0.1, 1.1, (7, 50))).to(dev)
+    yq = torch.from_numpy(rng.uniform(-1.2, 1.2, (7, 50))).to(dev)
+    for d in ((0, 0), (1, 0), (0, 2)):
+        first = ip(xq, yq, *d)           # general path; leaves the plan behind
+        assert tuple(d) in ip._plans
+        second = ip(xq, yq, *d)          # plan
+        out = torch.empty(7 * 50, dtype=torch.float64, device=dev)
+        third = ip(xq, yq, *d, out=out)  # plan, caller's result tensor
+        want = O.Interpolator2D(xk, yk, f, "cubic", (False, True))(xq.cpu().numpy().ravel(), yq.cpu().numpy().ravel(),
+                                                                   *d).reshape(7, 50)
+        assert second.shape == (7, 50) and third.shape == (7, 50) and third.data_ptr() == out.data_ptr()
+        assert same_bits(first.cpu().numpy(), second.cpu().numpy()) and same_bits(first.cpu().numpy(), third.cpu().numpy())
+        assert_parity(second.cpu().numpy(), want)
+    # not covered by the plan: float32 queries (promotion), NumPy queries, strided tensors
+    r32 = ip(xq.float(), yq.float())
+    assert r32.dtype == torch.float64
+    rnp = ip(xq.cpu().numpy(), yq.cpu().numpy())
+    assert isinstance(rnp, torch.Tensor) or isinstance(rnp, np.ndarray)
+    rs = ip(xq.t(), yq.t())
+    assert rs.shape == (50, 7) and same_bits(rs.t().cpu().numpy(), ip(xq, yq).cpu().numpy())
