@@ -242,6 +242,26 @@ int ipx_slopes_f64(const double* x, int32_t n, const double* f, int64_t outer, i
                    void* stream);
 
 /* ---------------------------------------------------------------------------------
+ * Reverse mode of the slope precompute with respect to f, for the methods that are linear in f:
+ * grad_f (+)= (d approx_df(x, f, method, axis) / d f)^T g, same (outer, n, inner) view.  This is the
+ * rule jax.grad derives by tracing interpax/_fd_derivs.py:79-101 (cubic), :303-324 (cardinal) and
+ * :160-300 (cubic2: a transposed tridiagonal solve; boundary VALUES do not depend on f), and what a
+ * gradient with respect to f of any cubic2 / cubic / cardinal interpolant chains behind
+ * ipx_vjp_tables_* (one call per link of the chain, in reverse).  accumulate != 0 adds into grad_f.
+ * g and grad_f must not alias.  IPX_SLOPE_MONOTONIC* / AKIMA* (not linear in f) and the two- /
+ * three-knot special systems of cubic2: IPX_EUNSUPPORTED.
+ * `workspace`: ipx_slopes_vjp_workspace_bytes(...) bytes of device memory.
+ * --------------------------------------------------------------------------------- */
+size_t ipx_slopes_vjp_workspace_bytes(int32_t method, int32_t n, int64_t outer, int64_t inner,
+                                      int32_t elem_size);
+int ipx_slopes_vjp_f32(const float* x, int32_t n, const float* g, int64_t outer, int64_t inner,
+                       int32_t method, const ipx_slope_opts* opts, int32_t accumulate, float* grad_f,
+                       void* workspace, void* stream);
+int ipx_slopes_vjp_f64(const double* x, int32_t n, const double* g, int64_t outer, int64_t inner,
+                       int32_t method, const ipx_slope_opts* opts, int32_t accumulate, double* grad_f,
+                       void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------
  * Periodic axis preparation -- the knot side of _make_periodic, interpax/_spline.py:
  * 1117-1122: xm = x % |period|; perm = stable argsort(xm); xpad = [xs[-1]-P, xs..., xs[0]+P].
  * xpad has n+2 entries, perm n.  `workspace` holds (n + 4) * elem_size bytes.

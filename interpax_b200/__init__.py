@@ -15,11 +15,13 @@ from .api import (
     Interpolator2D,
     Interpolator3D,
     approx_df,
+    approx_df_vjp,
     bin_index,
     interp1d,
     interp2d,
     interp3d,
     jvp_knots,
+    vjp_f,
     vjp_knots,
     vjp_tables,
 )
@@ -32,6 +34,7 @@ __all__ = [
     "PchipInterpolator",
     "PPoly",
     "approx_df",
+    "approx_df_vjp",
     "bin_index",
     "Interpolator1D",
     "Interpolator2D",
@@ -40,6 +43,7 @@ __all__ = [
     "interp2d",
     "interp3d",
     "jvp_knots",
+    "vjp_f",
     "vjp_knots",
     "vjp_tables",
 ]

@@ -63,12 +63,12 @@ class SlopeOpts(C.Structure):
 
 # every symbol include/ipx.h declares; tests/test_abi.py checks the .so exports them all
 SYMBOLS = (
-    ["ipx_version", "ipx_build_info", "ipx_slopes_workspace_bytes", "ipx_cell_order_workspace_bytes",
+    ["ipx_version", "ipx_build_info", "ipx_slopes_workspace_bytes", "ipx_slopes_vjp_workspace_bytes", "ipx_cell_order_workspace_bytes",
      "ipx_cell_sort_workspace_bytes", "ipx_halo_table_elems", "ipx_launch_count"]
     + [f"ipx_eval{d}d_{t}" for d in (1, 2, 3) for t in ("f32", "f64")]
     + [
         f"ipx_{name}_{t}"
-        for name in ("bin_index", "slopes", "slopes_pack", "periodic_knots", "pad_periodic", "pack", "cell_order", "cell_sort", "gather", "halo_table", "eval_stencil",
+        for name in ("bin_index", "slopes", "slopes_vjp", "slopes_pack", "periodic_knots", "pad_periodic", "pack", "cell_order", "cell_sort", "gather", "halo_table", "eval_stencil",
                      "gather_multi", "scatter", "vjp_tables", "vjp_stencil", "jvp_stencil", "ppoly_eval", "ppoly_pack", "ppoly_from_hermite",
                      "ppoly_derivative", "ppoly_antiderivative")
         for t in ("f32", "f64")
@@ -97,6 +97,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.ipx_build_info.argtypes = []
     lib.ipx_slopes_workspace_bytes.restype = C.c_size_t
     lib.ipx_slopes_workspace_bytes.argtypes = [i32, i32, i32]
+    lib.ipx_slopes_vjp_workspace_bytes.restype = C.c_size_t
+    lib.ipx_slopes_vjp_workspace_bytes.argtypes = [i32, i32, i64, i64, i32]
     lib.ipx_launch_count.restype = C.c_uint64
     lib.ipx_launch_count.argtypes = []
     lib.ipx_halo_table_elems.restype = C.c_int64
@@ -129,6 +131,9 @@ def _declare(lib: C.CDLL) -> None:
         f = getattr(lib, f"ipx_slopes_{t}")
         f.restype = C.c_int
         f.argtypes = [vp, i32, vp, i64, i64, i32, C.POINTER(SlopeOpts), vp, vp, vp]
+        f = getattr(lib, f"ipx_slopes_vjp_{t}")
+        f.restype = C.c_int
+        f.argtypes = [vp, i32, vp, i64, i64, i32, C.POINTER(SlopeOpts), i32, vp, vp, vp]
         f = getattr(lib, f"ipx_periodic_knots_{t}")
         f.restype = C.c_int
         f.argtypes = [vp, i32, C.c_double, vp, vp, vp, vp]

@@ -909,6 +909,140 @@ def vjp_tables(qs, knots, fshape, cotangent, method="cubic", derivative=0, extra
     return out if io.want_torch else {k: v.cpu().numpy() for k, v in out.items()}
 
 
+def _slope_opts(method, kwargs):
+    """ipx_slope_opts of a reverse-mode call: tension and boundary KINDS (the boundary values are
+    constants of the map f -> slopes and drop out of its transpose)."""
+    opts = L.SlopeOpts()
+    opts.c = float(kwargs.get("c", 0)) if method == "cardinal" else 0.0
+    if method == "cubic2":
+        bc = kwargs.get("bc_type", "not-a-knot")
+        kinds = []
+        for b in ((bc, bc) if isinstance(bc, str) else tuple(bc)):
+            if isinstance(b, str):
+                errorif(b not in ("clamped", "natural", "not-a-knot"), ValueError, f"bc_type={b} is not allowed.")
+                kinds.append({"clamped": L.IPX_BC_FIRST, "natural": L.IPX_BC_SECOND,
+                              "not-a-knot": L.IPX_BC_NOT_A_KNOT}[b])
+            else:
+                errorif(b[0] not in (1, 2), ValueError, "The specified derivative order must be 1 or 2.")
+                kinds.append(L.IPX_BC_FIRST if b[0] == 1 else L.IPX_BC_SECOND)
+        errorif(len(kinds) != 2, ValueError, "`bc_type` must contain 2 elements to specify start and end conditions.")
+        opts.bc_start, opts.bc_end = kinds
+    return opts
+
+
+def _slopes_vjp_dev(x: torch.Tensor, g: torch.Tensor, method: str, axis: int, kwargs: dict,
+                    into: torch.Tensor | None = None) -> torch.Tensor:
+    """(d approx_df / d f)^T g on device tensors; adds into ``into`` if given."""
+    errorif(method not in ("cubic", "cubic2", "cardinal", "catmull-rom"), NotImplementedError,
+            "approx_df is linear in f for method = cubic, cubic2, cardinal, catmull-rom only; "
+            "monotonic and akima have no transpose here")
+    lib = L.load()
+    axis = axis % g.ndim
+    n = g.shape[axis]
+    errorif(x.ndim != 1 or x.shape[0] != n, ValueError, "x and f must be arrays of equal length")
+    outer = int(np.prod(g.shape[:axis], dtype=np.int64))
+    inner = int(np.prod(g.shape[axis + 1:], dtype=np.int64))
+    code = _SLOPE_CODE[method]
+    opts = _slope_opts(method, kwargs)
+    g = g.contiguous()
+    out = torch.empty_like(g) if into is None else into
+    wbytes = lib.ipx_slopes_vjp_workspace_bytes(code, n, outer, inner, g.element_size())
+    ws = torch.empty(max(int(wbytes), 16), dtype=torch.uint8, device=g.device)
+    fn = getattr(lib, f"ipx_slopes_vjp_{_suffix(g)}")
+    L.check(fn(_ptr(x), n, _ptr(g), outer, inner, code, C.byref(opts), 0 if into is None else 1, _ptr(out),
+               _ptr(ws), _stream()), "ipx_slopes_vjp")
+    return out
+
+
+def approx_df_vjp(x, cotangent, method="cubic", axis=-1, **kwargs):
+    """Reverse-mode rule of ``approx_df(x, f, method, axis)`` with respect to ``f``: the transpose of
+    the (linear) slope map applied to ``cotangent`` (an array of the shape of ``f``).  method = cubic,
+    cubic2 (``bc_type`` as for ``approx_df``; boundary values are constants), cardinal, catmull-rom.
+    What ``jax.vjp(lambda f: approx_df(x, f, method, axis), f)[1]`` returns in the reference
+    (_fd_derivs.py:79-101, 160-300, 303-324)."""
+    want_torch = isinstance(x, torch.Tensor) or isinstance(cotangent, torch.Tensor)
+    dev = _device()
+    xdt = _promote([x])
+    gdt = np.dtype(np.result_type(_promote([cotangent]), xdt))
+    errorif(np.issubdtype(gdt, np.complexfloating), NotImplementedError,
+            "complex cotangents: pass real and imaginary parts separately")
+    rdt = np.dtype(np.float64) if gdt == np.float64 else np.dtype(np.float32)
+    gt = _to_dev(cotangent, rdt, dev)
+    xt = _to_dev(x, xdt, dev).to(_NP2T[rdt])
+    out = _slopes_vjp_dev(xt, gt, method, axis % gt.ndim, kwargs)
+    return out if want_torch else out.cpu().numpy()
+
+
+def vjp_f(qs, knots, fshape, cotangent, method="cubic", derivative=0, extrap=False, period=None,
+          functional=True, **kwargs):
+    """Reverse-mode rule of ``interp{1,2,3}d(q, knots, f, method)`` (``functional=True``) or
+    ``Interpolator{1,2,3}D(knots, f, method)(q)`` (``functional=False``) with respect to ``f``, the
+    slope chain included, for every method that is linear in ``f``: linear, cubic, cubic2 (any
+    ``bc_type``), cardinal, catmull-rom.  The transpose of the evaluation with respect to its 2^d
+    tables (``vjp_tables``) is followed by the transposed links of the reference's slope chain in
+    reverse order (_spline.py:1027-1040: fxyz <- fxy <- fx <- f ...), each a transposed stencil or,
+    for cubic2, a transposed tridiagonal solve.  On periodic axes the functional form takes its
+    slopes on the padded tables (_spline.py:924-938): the chain runs on the padded shape and the pad
+    is transposed last.  Returns the gradient, an array of shape ``fshape``."""
+    ndim = len(knots)
+    errorif(ndim not in (1, 2, 3) or len(qs) != ndim, ValueError, "need 1, 2 or 3 query and knot arrays")
+    errorif(method not in ("linear", "cubic", "cubic2", "cardinal", "catmull-rom"), NotImplementedError,
+            "the evaluation is linear in f for method = linear, cubic, cubic2, cardinal, catmull-rom; "
+            "nearest, monotonic and akima are not covered")
+    fshape = tuple(int(v) for v in fshape)
+    _check_shapes(ndim, knots, fshape)
+    io = _Inputs(qs, knots, cotangent)
+    errorif(io.complex, NotImplementedError, "complex cotangents: pass real and imaginary parts separately")
+    kn = [io.coords(k) for k in knots]
+    qd, qshape, _ = io.queries(qs)
+    qd = [q.to(io.dev) for q in qd]
+    batch = int(np.prod(fshape[ndim:], dtype=np.int64))
+    cot = _to_dev(cotangent, io.rdt, io.dev).reshape(-1)
+    errorif(cot.numel() != qd[0].numel() * batch, ValueError, "cotangent must have the shape of the output")
+    periods = _parse_ndarg(period, ndim)
+    params = _make_params(ndim, _parse_ndarg(derivative, ndim), _parse_extrap(extrap, ndim), periods)
+    mclass = _method_class(method)
+    names = TABLES[ndim] if mclass == L.IPX_CUBIC else ("f",)
+    pad_first = functional and mclass == L.IPX_CUBIC
+    mask, perms, kuse, pshape = 0, [None] * ndim, list(kn), list(fshape)
+    pk = [None] * ndim
+    for ax in range(ndim):
+        if periods[ax] is None:
+            continue
+        pk[ax] = _periodic_knots_dev(kn[ax], periods[ax])
+        kuse[ax] = pk[ax][0]
+        if pad_first:
+            mask |= L.IPX_WRAP_ONLY(ax)
+            pshape[ax] += 2
+        else:
+            perms[ax] = pk[ax][1]
+            mask |= L.IPX_PERIODIC(ax)
+    grads = [torch.zeros(pshape, dtype=io.tdt, device=io.dev) for _ in names]
+    narr = (C.c_int32 * ndim)(*[int(pshape[ax]) for ax in range(ndim)])
+    fn = getattr(L.load(), f"ipx_vjp_tables_{_suffix(qd[0])}")
+    L.check(fn(ndim, _ptr_array(qd), qd[0].numel(), _ptr_array(kuse), _ptr_array(perms), narr, batch, mclass,
+               mask, C.byref(params), 0, _ptr(cot), _ptr_array(grads), _stream()), "ipx_vjp_tables")
+    g = dict(zip(names, grads))
+    if mclass == L.IPX_CUBIC:
+        # slopes are taken on the padded knots (functional form) or on the caller's (classes)
+        sk = [kuse[ax] if (pad_first and pk[ax] is not None) else kn[ax] for ax in range(ndim)]
+        for name, src, ax in reversed(CHAIN[ndim]):
+            _slopes_vjp_dev(sk[ax], g[name], method, ax, kwargs, into=g[src])
+    gf = g["f"]
+    if pad_first:
+        # transpose of the wrap pad (_spline.py:1123-1135): padded row u holds f[perm[(u-1) mod n]]
+        for ax in range(ndim):
+            if pk[ax] is None:
+                continue
+            n = fshape[ax]
+            perm = pk[ax][1].to(torch.int64)
+            src = perm[(torch.arange(n + 2, device=io.dev) - 1) % n]
+            shape = list(gf.shape)
+            shape[ax] = n
+            gf = torch.zeros(shape, dtype=gf.dtype, device=gf.device).index_add_(ax, src, gf)
+    return gf if io.want_torch else gf.cpu().numpy()
+
+
 def _grad_stencil_setup(qs, knots, f, method, derivative, extrap, period, functional, kwargs, dtype_item):
     ndim = len(knots)
     errorif(ndim not in (1, 2, 3) or len(qs) != ndim, ValueError, "need 1, 2 or 3 query and knot arrays")

@@ -1034,7 +1034,195 @@ static int launch_slopes_pack(int32_t ndim, const T* const* knots, const int32_t
   }
 }
 
+// ------------------------------------------------------------------ reverse mode of approx_df
+// For the methods that are LINEAR in f -- cubic (_fd_derivs.py:79-101), cardinal / catmull-rom
+// (:303-324) and cubic2 (:160-300: slopes = T^-1 b(f), T from the knots and boundary kinds only,
+// b linear in f plus a boundary-value constant) -- the slope map along one axis is
+//   slopes = M f + const,   M = R (local) or T^-1 R (cubic2),
+// with every row of R supported on at most three consecutive nodes.  Its transpose, which is what
+// jax.grad of anything built on approx_df needs (tests/test_interpolate.py:542-637 differentiate
+// through it), is grad_f = R^T y with y = g (local) or the solution of T^T y = g (cubic2).
+
+// row k of R as (first node j0, three coefficients); rows of a masked (duplicate-knot) cubic2
+// equation and rows that hold a boundary VALUE are zero
+template <typename T>
+__device__ __forceinline__ void slope_row(const T* __restrict__ x, int n, int method, T one_minus_c,
+                                          int bs, int be, int k, int& j0, T (&c)[3]) {
+  auto h = [&](int j) { return x[j + 1] - x[j]; };
+  auto r = [&](int j) { return safe_recip(x[j + 1] - x[j]); };
+  c[0] = c[1] = c[2] = T(0);
+  const int jend = n >= 3 ? n - 3 : 0;     // window of the last row
+  const int pa = n - 2 - jend, pb = n - 1 - jend;  // slots of f[n-2], f[n-1] in it
+  if (method == IPX_SLOPE_CUBIC) {
+    if (k == 0) { j0 = 0; c[0] = -r(0); c[1] = r(0); }
+    else if (k == n - 1) { j0 = jend; c[pa] = -r(n - 2); c[pb] = r(n - 2); }
+    else { j0 = k - 1; c[0] = T(-0.5) * r(k - 1); c[1] = T(0.5) * (r(k - 1) - r(k)); c[2] = T(0.5) * r(k); }
+    return;
+  }
+  if (method == IPX_SLOPE_CARDINAL) {
+    if (k == 0) { j0 = 0; c[0] = -one_minus_c * r(0); c[1] = one_minus_c * r(0); }
+    else if (k == n - 1) { j0 = jend; c[pa] = -one_minus_c * r(n - 2); c[pb] = one_minus_c * r(n - 2); }
+    else { j0 = k - 1; const T R = one_minus_c * safe_recip(x[k + 1] - x[k - 1]); c[0] = -R; c[2] = R; }
+    return;
+  }
+  // cubic2: the right-hand side b_k(f) of cubic2_rhs
+  T lo, di, up;
+  bool masked;
+  cubic2_row(x, n, bs, be, k, lo, di, up, masked);
+  if (k == 0) {
+    j0 = 0;
+    if (masked) return;
+    if (bs == IPX_BC_NOT_A_KNOT) {
+      const T d = x[2] - x[0];
+      const T A = (h(0) + T(2) * d) * h(1) * r(0) / d, B = h(0) * h(0) * r(1) / d;
+      c[0] = -A; c[1] = A - B; c[2] = B;
+    } else if (bs == IPX_BC_SECOND) { c[0] = T(-3); c[1] = T(3); }
+    return;
+  }
+  if (k == n - 1) {
+    j0 = jend;
+    if (masked) return;
+    if (be == IPX_BC_NOT_A_KNOT) {
+      const T d = x[n - 1] - x[n - 3];
+      const T A = h(n - 2) * h(n - 2) * r(n - 3) / d, B = (T(2) * d + h(n - 2)) * h(n - 3) * r(n - 2) / d;
+      c[0] = -A; c[1] = A - B; c[2] = B;
+    } else if (be == IPX_BC_SECOND) { c[pa] = T(-3); c[pb] = T(3); }
+    return;
+  }
+  j0 = k - 1;
+  if (masked) return;
+  const T A = T(3) * h(k) * r(k - 1), B = T(3) * h(k - 1) * r(k);
+  c[0] = -A; c[1] = A - B; c[2] = B;
+}
+
+// knot-only part of the Thomas recurrence for T^T (sub-diagonal of row k = upper_{k-1} of T,
+// super-diagonal = lower_{k+1} of T); ws[0..n) = c', ws[n..2n) = den
+template <typename T>
+__global__ void cubic2_factor_T_kernel(const T* __restrict__ x, int n, int bs, int be, T* __restrict__ ws) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  T cprev = T(0), up_prev = T(0);
+  for (int k = 0; k < n; ++k) {
+    T lo, di, up, lo_next = T(0), d2, u2;
+    bool masked;
+    cubic2_row(x, n, bs, be, k, lo, di, up, masked);
+    if (k + 1 < n) cubic2_row(x, n, bs, be, k + 1, lo_next, d2, u2, masked);
+    const T den = di - up_prev * cprev;
+    cprev = lo_next / den;
+    ws[k] = cprev;
+    ws[n + k] = den;
+    ws[2 * n + k] = up_prev;  // sub-diagonal of T^T
+    up_prev = up;
+  }
+}
+
+// y = T^-T g, one thread per column, into `y` (same (outer, n, inner) view as g)
+template <typename T>
+__global__ void cubic2_solve_T_kernel(const T* __restrict__ g, T* __restrict__ y, int64_t outer, int64_t inner,
+                                      int n, const T* __restrict__ ws) {
+  const int64_t cols = outer * inner;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; col < cols; col += stride) {
+    const int64_t o = col / inner, i = col - o * inner;
+    const int64_t base = o * n * inner + i;
+    T dprev = T(0);
+    for (int k = 0; k < n; ++k) {
+      dprev = (g[base + (int64_t)k * inner] - ws[2 * n + k] * dprev) / ws[n + k];
+      y[base + (int64_t)k * inner] = dprev;
+    }
+    T ynext = T(0);
+    for (int k = n - 1; k >= 0; --k) {
+      ynext = y[base + (int64_t)k * inner] - ws[k] * ynext;
+      y[base + (int64_t)k * inner] = ynext;
+    }
+  }
+}
+
+// grad_f[j] (+)= sum_k y[k] R[k][j]: one thread per element, rows j-1 .. j+1 and the two end rows
+template <typename T>
+__global__ void slopes_rowsT_kernel(const T* __restrict__ x, const T* __restrict__ y, T* __restrict__ gf,
+                                    int64_t outer, int64_t inner, int n, int method, T one_minus_c, int bs, int be,
+                                    int accumulate) {
+  const int64_t total = outer * n * inner;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int64_t i = e % inner, rr = e / inner;
+    const int j = (int)(rr % n);
+    const int64_t base = (rr / n) * n * inner + i;
+    T acc = T(0);
+    auto add_row = [&](int k) {
+      int j0;
+      T c[3];
+      slope_row(x, n, method, one_minus_c, bs, be, k, j0, c);
+      const int p = j - j0;
+      if (p >= 0 && p < 3) acc += c[p] * y[base + (int64_t)k * inner];
+    };
+    for (int k = j - 1; k <= j + 1; ++k)
+      if (k >= 1 && k <= n - 2) add_row(k);
+    add_row(0);
+    if (n > 1) add_row(n - 1);
+    gf[e] = accumulate ? gf[e] + acc : acc;
+  }
+}
+
+template <typename T>
+static int launch_slopes_vjp(const T* x, int32_t n, const T* g, int64_t outer, int64_t inner, int32_t method,
+                             const ipx_slope_opts* opts, int32_t accumulate, T* grad_f, void* workspace,
+                             void* stream) {
+  if (outer < 0 || inner < 0 || n < 0) return IPX_EINVAL;
+  const int64_t total = outer * n * inner;
+  if (total == 0) return IPX_OK;
+  if (x == nullptr || g == nullptr || grad_f == nullptr || g == grad_f) return IPX_EINVAL;
+  if (n < 2) return IPX_EINVAL;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = slope_grid(total);
+  const T omc = T(1) - (opts ? T(opts->c) : T(0));
+  switch (method) {
+    case IPX_SLOPE_ZERO:
+      if (!accumulate) { fill_zero_kernel<T><<<grid, kSlopeThreads, 0, s>>>(grad_f, total); count_launches(1); }
+      break;
+    case IPX_SLOPE_CUBIC:
+    case IPX_SLOPE_CARDINAL:
+      slopes_rowsT_kernel<T><<<grid, kSlopeThreads, 0, s>>>(x, g, grad_f, outer, inner, n, method, omc, 0, 0, accumulate);
+      count_launches(1);
+      break;
+    case IPX_SLOPE_CUBIC2: {
+      const int bs = opts ? opts->bc_start : IPX_BC_NOT_A_KNOT, be = opts ? opts->bc_end : IPX_BC_NOT_A_KNOT;
+      if (bs < 0 || bs > 2 || be < 0 || be > 2) return IPX_EINVAL;
+      // the two-knot and three-knot parabola cases of the forward pass are separate small systems
+      if (n == 2 || (n == 3 && bs == IPX_BC_NOT_A_KNOT && be == IPX_BC_NOT_A_KNOT)) return IPX_EUNSUPPORTED;
+      if (workspace == nullptr) return IPX_EINVAL;
+      T* ws = static_cast<T*>(workspace);
+      T* y = ws + 3 * (size_t)n;  // + one table-sized scratch for y
+      cubic2_factor_T_kernel<T><<<1, 32, 0, s>>>(x, n, bs, be, ws); count_launches(1);
+      cubic2_solve_T_kernel<T><<<slope_grid(outer * inner), kSlopeThreads, 0, s>>>(g, y, outer, inner, n, ws);
+      count_launches(1);
+      slopes_rowsT_kernel<T><<<grid, kSlopeThreads, 0, s>>>(x, y, grad_f, outer, inner, n, method, omc, bs, be, accumulate);
+      count_launches(1);
+      break;
+    }
+    default:  // monotonic, akima: not linear in f
+      return (method >= 0 && method <= IPX_SLOPE_AKIMA_COMPLEX) ? IPX_EUNSUPPORTED : IPX_EINVAL;
+  }
+  return cudaPeekAtLastError() == cudaSuccess ? IPX_OK : IPX_ELAUNCH;
+}
+
 }  // namespace ipx
+
+extern "C" size_t ipx_slopes_vjp_workspace_bytes(int32_t method, int32_t n, int64_t outer, int64_t inner,
+                                                 int32_t elem_size) {
+  if (method != IPX_SLOPE_CUBIC2 || n <= 0 || outer <= 0 || inner <= 0) return 16;
+  return ((size_t)3 * (size_t)n + (size_t)outer * (size_t)n * (size_t)inner) * (size_t)elem_size + 16;
+}
+extern "C" int ipx_slopes_vjp_f32(const float* x, int32_t n, const float* g, int64_t outer, int64_t inner,
+                                  int32_t method, const ipx_slope_opts* opts, int32_t accumulate,
+                                  float* grad_f, void* workspace, void* stream) {
+  return ipx::launch_slopes_vjp<float>(x, n, g, outer, inner, method, opts, accumulate, grad_f, workspace, stream);
+}
+extern "C" int ipx_slopes_vjp_f64(const double* x, int32_t n, const double* g, int64_t outer, int64_t inner,
+                                  int32_t method, const ipx_slope_opts* opts, int32_t accumulate,
+                                  double* grad_f, void* workspace, void* stream) {
+  return ipx::launch_slopes_vjp<double>(x, n, g, outer, inner, method, opts, accumulate, grad_f, workspace, stream);
+}
 
 extern "C" int ipx_slopes_pack_f32(int32_t ndim, const float* const* knots, const int32_t* n,
                                    const float* f, int64_t batch, int32_t method,

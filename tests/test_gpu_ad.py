@@ -154,3 +154,123 @@ def test_knot_and_table_derivatives_general(ndim):
                 smooth &= cell == ref_cell
         scale = np.abs(num[smooth]).max()
         np.testing.assert_allclose(tan[smooth], num[smooth], rtol=2e-5, atol=2e-6 * scale, err_msg=what)
+
+
+BC_PAIRS = ["not-a-knot", "natural", "clamped", ("not-a-knot", "natural"), ("clamped", "not-a-knot"),
+            ((1, 0.7), (2, -0.4)), ((2, 0.3), "not-a-knot")]
+
+
+@pytest.mark.parametrize("method", ["cubic", "cardinal", "catmull-rom", "cubic2"])
+def test_approx_df_vjp_is_the_transpose_of_approx_df(method):
+    """approx_df is affine in f for these methods (_fd_derivs.py:79-101, 160-300, 303-324); its
+    reverse rule must satisfy <g, D v> == <D^T g, v> with D v taken from the ORACLE, for every axis
+    position, non-uniform knots, every boundary-condition pair of cubic2, a duplicated knot, and
+    must reproduce the dense transpose column by column on a small case."""
+    rng = np.random.default_rng(77)
+    bcs = BC_PAIRS if method == "cubic2" else [None]
+    for bc in bcs:
+        for shape, axis in (((11,), 0), ((4, 9, 3), 1), ((5, 8), -1), ((7, 6), 0), ((3,), 0) if bc != "not-a-knot" else ((4,), 0)):
+            n = shape[axis]
+            x = np.sort(rng.uniform(0.0, 3.0, n))
+            if n >= 9:
+                x[5] = x[4]  # duplicate knot: the row is neutralised (_fd_derivs.py:281-286)
+            kw = {"c": 0.35} if method == "cardinal" else {}
+            kw0 = dict(kw)
+            if bc is not None:
+                def full(b, zero):
+                    if isinstance(b, tuple) and not isinstance(b[0], (str, tuple)):
+                        vshape = shape[:axis % len(shape)] + shape[axis % len(shape) + 1:]
+                        return (b[0], np.zeros(vshape) if zero else np.full(vshape, b[1]))
+                    return b
+                pair = (bc, bc) if isinstance(bc, str) else bc
+                kw["bc_type"] = tuple(full(b, False) for b in pair)
+                kw0["bc_type"] = tuple(full(b, True) for b in pair)
+            v = rng.normal(size=shape)
+            g = rng.normal(size=shape)
+            with np.errstate(all="ignore"):
+                Dv = O.approx_df(x, v, method, axis, **kw0)  # zero boundary values: the linear part
+            got = ipx.approx_df_vjp(x, g, method, axis, **kw)
+            assert got.shape == shape
+            lhs, rhs = float(np.sum(g * Dv)), float(np.sum(got * v))
+            assert abs(lhs - rhs) <= 1e-11 * max(1.0, abs(lhs), np.abs(g).max() * np.abs(Dv).max() * v.size), (method, bc, shape, axis)
+    # dense transpose, column by column
+    n = 8
+    x = np.sort(rng.uniform(0, 2, n))
+    kw = {"c": 0.2} if method == "cardinal" else {}
+    D = np.stack([O.approx_df(x, e, method, 0, **kw) for e in np.eye(n)], axis=1)  # D[k, j]
+    for k in range(n):
+        np.testing.assert_allclose(ipx.approx_df_vjp(x, np.eye(n)[k], method, 0, **kw), D[k], rtol=1e-12, atol=1e-13)
+    # float32 runs too
+    got32 = ipx.approx_df_vjp(x.astype(np.float32), np.eye(n, dtype=np.float32)[3], method, 0, **kw)
+    assert got32.dtype == np.float32
+    np.testing.assert_allclose(got32, D[3], rtol=2e-4, atol=2e-4 * np.abs(D).max())
+
+
+def test_approx_df_vjp_rejects_what_is_not_linear():
+    x = np.linspace(0, 1, 6)
+    for m in ("monotonic", "akima"):
+        with pytest.raises(NotImplementedError):
+            ipx.approx_df_vjp(x, np.ones(6), m)
+
+
+@pytest.mark.parametrize("ndim", [1, 2, 3])
+def test_vjp_f_is_the_transpose_of_the_evaluation(ndim):
+    """Gradient with respect to f with the slope chain inside, for every method linear in f
+    (cubic2 included: transposed tridiagonal solves along each axis of the chain), both periodic
+    conventions, derivative orders, extrapolation fills: <cot, J v> == <J^T cot, v> with J v from
+    the ORACLE's own evaluation of the tangent table (the map is linear in f), and for the local
+    stencils the same gradient as ipx.vjp_knots gives."""
+    rng = np.random.default_rng(500 + ndim)
+    ns = [9, 7, 8][:ndim]
+    nq = 400
+    for trial in range(12):
+        functional = trial % 2 == 0
+        method = ["cubic2", "cubic", "linear", "cardinal", "cubic2", "catmull-rom"][trial % 6]
+        kw = {"c": 0.25} if method == "cardinal" else {}
+        if method == "cubic2":
+            kw["bc_type"] = ["not-a-knot", "natural", ("clamped", "not-a-knot")][(trial // 2) % 3]
+        knots = [np.sort(rng.uniform(0.05, 2.0, n)) for n in ns]
+        for k in knots:
+            k[0] = 0.05
+        per_axes = [bool((trial >> 1) & 1) and ax != ndim - 1 for ax in range(ndim)] if ndim > 1 else [trial % 4 >= 2]
+        period = tuple(2.3 if p else None for p in per_axes)
+        period = period[0] if ndim == 1 else period
+        deriv = tuple(int(v) for v in rng.integers(0, 3, ndim)) if trial % 3 == 1 else (0,) * ndim
+        dfun = deriv[0] if ndim == 1 else deriv
+        extrap = [True, (True, 0.5), False][trial % 3]
+        qs = [rng.uniform(-0.3, 2.4, nq) for _ in range(ndim)]
+        what = f"nd={ndim} {method} functional={functional} per={period} d={deriv} ex={extrap} {kw}"
+        v = rng.normal(size=ns)
+        with np.errstate(all="ignore"):
+            if functional:
+                Jv = OFUN[ndim - 1](*qs, *knots, v, method, dfun, extrap, period, **kw)
+                J0 = OFUN[ndim - 1](*qs, *knots, np.zeros(ns), method, dfun, extrap, period, **kw)
+            else:
+                Jv = OCLS[ndim - 1](*knots, v, method, extrap, period, **kw)(*qs, *deriv)
+                J0 = OCLS[ndim - 1](*knots, np.zeros(ns), method, extrap, period, **kw)(*qs, *deriv)
+        Jv = Jv - J0  # a numeric fill value is a constant, not part of the linear map
+        ok = np.isfinite(Jv)
+        cot = rng.normal(size=nq)
+        cot[~ok] = 0.0
+        g = ipx.vjp_f(qs, knots, ns, cot, method, dfun, extrap, period, functional=functional, **kw)
+        assert g.shape == tuple(ns)
+        lhs, rhs = float(np.dot(cot[ok], Jv[ok])), float(np.sum(g * v))
+        assert abs(lhs - rhs) <= 1e-10 * max(1.0, abs(lhs), np.abs(Jv[ok]).max() * np.abs(cot).max()), what
+        if method in ("cubic", "cardinal", "catmull-rom") and not (
+                not functional and any(per_axes)):
+            g2 = ipx.vjp_knots(qs, knots, rng.normal(size=ns), cot, method, dfun, extrap, period,
+                               functional=functional, **kw)["f"]
+            np.testing.assert_allclose(g, g2, rtol=1e-10, atol=1e-11 * max(1.0, np.abs(g2).max()), err_msg=what)
+
+
+def test_vjp_f_batched_tables():
+    """Trailing batch dims of f: the gradient has the shape of f and each batch element its own."""
+    rng = np.random.default_rng(9)
+    x, y = np.sort(rng.uniform(0, 1, 10)), np.sort(rng.uniform(0, 1, 12))
+    qs = [rng.uniform(0, 1, 50), rng.uniform(0, 1, 50)]
+    fshape = (10, 12, 3)
+    cot = rng.normal(size=(50, 3))
+    g = ipx.vjp_f(qs, (x, y), fshape, cot, "cubic2")
+    for b in range(3):
+        gb = ipx.vjp_f(qs, (x, y), (10, 12), cot[:, b], "cubic2")
+        np.testing.assert_allclose(g[..., b], gb, rtol=1e-12, atol=1e-13)
