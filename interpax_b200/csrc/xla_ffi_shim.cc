@@ -264,6 +264,29 @@ ffi::Error SlopesImpl(cudaStream_t stream, ffi::AnyBuffer x, ffi::AnyBuffer f, f
   return to_error(rc, "ipx_slopes");
 }
 
+// ipx_slopes_vjp_*: operands x, g (cotangent of the slopes); results grad_f, workspace
+ffi::Error SlopesVjpImpl(cudaStream_t stream, ffi::AnyBuffer x, ffi::AnyBuffer g, ffi::Result<ffi::AnyBuffer> out,
+                         ffi::Result<ffi::AnyBuffer> ws, int32_t method, int32_t axis, double c, int32_t bc_start,
+                         int32_t bc_end) {
+  const auto d = g.dimensions();
+  if (axis < 0 || axis >= (int)d.size()) return bad("ipx_slopes_vjp: axis out of range");
+  const int64_t outer = product(d, 0, axis), inner = product(d, axis + 1, d.size());
+  ipx_slope_opts o;
+  o.c = c;
+  o.bc_start = bc_start;
+  o.bc_end = bc_end;
+  o.bc_start_value = nullptr;  // boundary values are constants of the map: not part of its transpose
+  o.bc_end_value = nullptr;
+  int rc = g.element_type() == ffi::F64
+               ? ipx_slopes_vjp_f64(static_cast<const double*>(x.untyped_data()), (int32_t)d[axis],
+                                    static_cast<const double*>(g.untyped_data()), outer, inner, method, &o, 0,
+                                    static_cast<double*>(out->untyped_data()), ws->untyped_data(), stream)
+               : ipx_slopes_vjp_f32(static_cast<const float*>(x.untyped_data()), (int32_t)d[axis],
+                                    static_cast<const float*>(g.untyped_data()), outer, inner, method, &o, 0,
+                                    static_cast<float*>(out->untyped_data()), ws->untyped_data(), stream);
+  return to_error(rc, "ipx_slopes_vjp");
+}
+
 // ---------------------------------------------------------------------------------------------
 // ipx_slopes_pack_* (fused chain -> records) and ipx_pack_* (tables -> records)
 // ---------------------------------------------------------------------------------------------
@@ -433,6 +456,18 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(IpxSlopes, SlopesImpl,
                                   .Ctx<Stream>()
                                   .Arg<ffi::AnyBuffer>()
                                   .Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Ret<ffi::AnyBuffer>()
+                                  .Ret<ffi::AnyBuffer>()
+                                  .Attr<int32_t>("method")
+                                  .Attr<int32_t>("axis")
+                                  .Attr<double>("c")
+                                  .Attr<int32_t>("bc_start")
+                                  .Attr<int32_t>("bc_end"));
+XLA_FFI_DEFINE_HANDLER_SYMBOL(IpxSlopesVjp, SlopesVjpImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<Stream>()
                                   .Arg<ffi::AnyBuffer>()
                                   .Arg<ffi::AnyBuffer>()
                                   .Ret<ffi::AnyBuffer>()

@@ -57,7 +57,7 @@ CHAIN = {1: (("fx", "f", 0),), 2: (("fx", "f", 0), ("fy", "f", 1), ("fxy", "fx",
          3: (("fx", "f", 0), ("fy", "f", 1), ("fz", "f", 2), ("fxy", "fx", 1), ("fxz", "fx", 2), ("fyz", "fy", 2),
              ("fxyz", "fxy", 2))}
 _HANDLERS = ("IpxEval", "IpxEvalStencil", "IpxHaloTable", "IpxSlopes", "IpxSlopesPack", "IpxPack",
-             "IpxPeriodicKnots", "IpxPadPeriodic", "IpxVjpTables", "IpxBinIndex")
+             "IpxPeriodicKnots", "IpxPadPeriodic", "IpxVjpTables", "IpxBinIndex", "IpxSlopesVjp")
 _registered = False
 
 
@@ -77,6 +77,9 @@ def _core():
     lib = ctypes.CDLL(_CORE)
     lib.ipx_halo_table_elems.restype = ctypes.c_int64
     lib.ipx_slopes_workspace_bytes.restype = ctypes.c_size_t
+    lib.ipx_slopes_vjp_workspace_bytes.restype = ctypes.c_size_t
+    lib.ipx_slopes_vjp_workspace_bytes.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64,
+                                                   ctypes.c_int32]
     return lib
 
 
@@ -166,12 +169,37 @@ def approx_df(x, f, method="cubic", axis=-1, **kwargs):
             kinds.append(1 if b[0] == 1 else 2)
             vals.append(jnp.asarray(b[1], dt).ravel())
     ws = int(_core().ipx_slopes_workspace_bytes(SLOPE[method], n, jnp.dtype(dt).itemsize))
-    out, _ = _call("IpxSlopes",
-                   (jax.ShapeDtypeStruct(f.shape, dt), jax.ShapeDtypeStruct((max(ws, 16),), jnp.uint8)),
-                   x, f, vals[0], vals[1], method=np.int32(SLOPE[method]), axis=np.int32(axis),
-                   c=np.float64(kwargs.get("c", 0.0) if method == "cardinal" else 0.0),
-                   bc_start=np.int32(kinds[0]), bc_end=np.int32(kinds[1]))
-    return out
+    attrs = dict(method=np.int32(SLOPE[method]), axis=np.int32(axis),
+                 c=np.float64(kwargs.get("c", 0.0) if method == "cardinal" else 0.0),
+                 bc_start=np.int32(kinds[0]), bc_end=np.int32(kinds[1]))
+
+    def forward(res, ff):
+        xx, v0, v1 = res
+        return _call("IpxSlopes",
+                     (jax.ShapeDtypeStruct(f.shape, dt), jax.ShapeDtypeStruct((max(ws, 16),), jnp.uint8)),
+                     xx, ff, v0, v1, **attrs)[0]
+
+    if method not in ("cubic", "cubic2", "cardinal", "catmull-rom"):
+        return forward((x, vals[0], vals[1]), f)  # monotonic / akima: not linear in f, no AD rule here
+
+    # linear in f (plus a constant from the boundary values): reverse mode = ipx_slopes_vjp_*
+    # (transposed stencils; cubic2: transposed tridiagonal solve).  The boundary-value constant is
+    # added outside the linear call.
+    def transpose(res, ct):
+        xx = res[0]
+        wsv = int(_core().ipx_slopes_vjp_workspace_bytes(SLOPE[method], n, int(np.prod(f.shape[:axis], dtype=np.int64)),
+                                                         int(np.prod(f.shape[axis + 1:], dtype=np.int64)),
+                                                         jnp.dtype(dt).itemsize))
+        return _call("IpxSlopesVjp",
+                     (jax.ShapeDtypeStruct(f.shape, dt), jax.ShapeDtypeStruct((max(wsv, 16),), jnp.uint8)),
+                     xx, ct, **attrs)[0]
+
+    zeros = (x, jnp.zeros_like(vals[0]), jnp.zeros_like(vals[1]))
+    lin = linear_call(forward, transpose, zeros, f)
+    if vals[0].size or vals[1].size:
+        const = jax.lax.stop_gradient(forward((x, vals[0], vals[1]), jnp.zeros_like(f)))
+        return lin + const
+    return lin
 
 
 def periodic_knots(x, period):
