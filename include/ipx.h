@@ -403,6 +403,38 @@ IPX_DECL_GRAD(f32, float)
 IPX_DECL_GRAD(f64, double)
 
 /* ---------------------------------------------------------------------------------
+ * Reverse mode with respect to the knots for the TABLE form of the cubic evaluation and for the
+ * slope precompute -- the pieces from which the knot gradient of cubic2 (a global solve) and
+ * monotonic (not linear in f) interpolants is chained, the two methods of the reference's TestAD
+ * (tests/test_interpolate.py:542-637) that ipx_vjp_stencil_* does not cover.
+ *
+ * ipx_vjp_knots_tables_*: grad_knots[ax][k] += sum_q cotangent[q] * d out[q] / d knots[ax][k] with the
+ *   2^ndim tables held FIXED (the dependence of _spline.py:576-589, 770-800, 1055-1099 on the cell's
+ *   two knots: local coordinate and the dx that scales the slope tables).  Arguments as for
+ *   ipx_vjp_tables_* (IPX_CUBIC, scalar-valued tables in the reference's stacking order, SoA);
+ *   grad_knots: HOST array of ndim device pointers (entries may be NULL), each over the nk LOOKUP
+ *   knots of its axis (n, or the n + 2 padded knots of a periodic axis).  Accumulates.
+ * ipx_slopes_knots_vjp_*: one link of the slope chain, slopes = approx_df(x, f, method) along the
+ *   middle axis of the (outer, n, inner) view: grad_x[k] += sum y * d slopes / d x[k]; for
+ *   IPX_SLOPE_MONOTONIC* also grad_f += (d slopes / d f)^T y (that method is not linear in f, so
+ *   ipx_slopes_vjp_* does not serve it).  y is the cotangent of the slopes, except for
+ *   IPX_SLOPE_CUBIC2, where it is T^-T applied to that cotangent -- the array ipx_slopes_vjp_*
+ *   leaves in its workspace at element offset 3 n -- and `slopes` must hold the forward result of
+ *   the link (NULL otherwise).  opts as in the forward call (boundary values included).  n >= 3.
+ * --------------------------------------------------------------------------------- */
+#define IPX_DECL_GRAD_TABLES(SUF, T)                                                                      \
+  int ipx_vjp_knots_tables_##SUF(int32_t ndim, const T* const* q, int64_t nq, const T* const* knots,      \
+                                 const int32_t* const* perm, const int32_t* n, const T* const* tables,    \
+                                 int32_t periodic_mask, const ipx_params* params,                         \
+                                 int32_t params_on_device, const T* cotangent, T* const* grad_knots,      \
+                                 void* stream);                                                           \
+  int ipx_slopes_knots_vjp_##SUF(const T* x, int32_t n, const T* f, const T* slopes, const T* y,          \
+                                 int64_t outer, int64_t inner, int32_t method, const ipx_slope_opts* opts,\
+                                 T* grad_x, T* grad_f, void* stream);
+IPX_DECL_GRAD_TABLES(f32, float)
+IPX_DECL_GRAD_TABLES(f64, double)
+
+/* ---------------------------------------------------------------------------------
  * Piecewise polynomials in the power basis (interpax/_ppoly.py).  Coefficients as the
  * reference holds them after its moveaxis: c[(j*m + i)*batch + b] multiplies
  * (x - x[i])^(k-1-j) on piece i, for trailing element b; x has m+1 breakpoints.

@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libipx.so")
-SOURCES = ["ipx_eval.cu", "ipx_stencil.cu", "ipx_grad.cu", "ipx_slopes.cu", "ipx_prep.cu", "ipx_sort.cu", "ipx_vjp.cu", "ipx_ppoly.cu"]
+SOURCES = ["ipx_eval.cu", "ipx_stencil.cu", "ipx_grad.cu", "ipx_grad_tables.cu", "ipx_slopes.cu", "ipx_prep.cu", "ipx_sort.cu", "ipx_vjp.cu", "ipx_ppoly.cu"]
 HEADERS = [os.path.join(CSRC, "ipx_device.cuh"), os.path.join(CSRC, "ipx_internal.cuh"), os.path.join(CSRC, "ipx_halo.cuh"), os.path.join(CSRC, "ipx_stencil_col.cuh"), os.path.join(CSRC, "ipx_eval_tile.cuh"), os.path.join(CSRC, "ipx_contract.cuh"), os.path.join(CSRC, "ipx_eval_rows.cuh"),
            os.path.join(HERE, "..", "include", "ipx.h")]
 NVCC_FLAGS = [

@@ -211,6 +211,21 @@ def _slopes_dev(x: torch.Tensor, f: torch.Tensor, method: str, axis: int, kwargs
     if cplx and method == "akima":
         errorif(axis == f.ndim - 1, ValueError, "the (re, im) pair axis cannot be differentiated")
         code = L.IPX_SLOPE_AKIMA_COMPLEX
+    opts, keep = _slope_opts_values(f, method, axis, kwargs, cplx)
+    out = torch.empty_like(f)
+    elem = f.element_size()
+    wbytes = lib.ipx_slopes_workspace_bytes(code, n, elem)
+    ws = torch.empty(max(int(wbytes), 16), dtype=torch.uint8, device=f.device)
+    fn = getattr(lib, f"ipx_slopes_{_suffix(f)}")
+    L.check(
+        fn(_ptr(x), n, _ptr(f), outer, inner, code, C.byref(opts), _ptr(out), _ptr(ws), _stream()),
+        "ipx_slopes",
+    )
+    return out
+
+
+def _slope_opts_values(f: torch.Tensor, method: str, axis: int, kwargs: dict, cplx: bool = False):
+    """ipx_slope_opts of a forward call (tension, boundary kinds and VALUES) + the tensors it points to."""
     opts = L.SlopeOpts()
     opts.c = float(kwargs.get("c", 0)) if method == "cardinal" else 0.0
     keep = []
@@ -233,16 +248,7 @@ def _slopes_dev(x: torch.Tensor, f: torch.Tensor, method: str, axis: int, kwargs
                 vals.append(v.data_ptr())
         opts.bc_start, opts.bc_end = kinds
         opts.bc_start_value, opts.bc_end_value = vals
-    out = torch.empty_like(f)
-    elem = f.element_size()
-    wbytes = lib.ipx_slopes_workspace_bytes(code, n, elem)
-    ws = torch.empty(max(int(wbytes), 16), dtype=torch.uint8, device=f.device)
-    fn = getattr(lib, f"ipx_slopes_{_suffix(f)}")
-    L.check(
-        fn(_ptr(x), n, _ptr(f), outer, inner, code, C.byref(opts), _ptr(out), _ptr(ws), _stream()),
-        "ipx_slopes",
-    )
-    return out
+    return opts, keep
 
 
 def _validate_bc(bc_type, expected_shape):
@@ -1080,6 +1086,121 @@ def _grad_stencil_setup(qs, knots, f, method, derivative, extrap, period, functi
     return io, ndim, qd, qshape, kn, kuse, perms, ft, params, mask, code, c, narr
 
 
+_CHAIN_KNOT_METHODS = ("cubic2", "monotonic", "monotonic-0")
+
+
+def _link_vjp(x, src, slopes, g, method, axis, kwargs, g_src, g_x):
+    """Reverse rule of one link ``slopes = approx_df(x, src, method, axis)``: adds (d slopes/d src)^T g
+    into ``g_src`` and (d slopes/d x)^T g into ``g_x``."""
+    lib = L.load()
+    n = src.shape[axis]
+    outer = int(np.prod(src.shape[:axis], dtype=np.int64))
+    inner = int(np.prod(src.shape[axis + 1:], dtype=np.int64))
+    code = _SLOPE_CODE[method]
+    opts, keep = _slope_opts_values(src, method, axis, kwargs)
+    suf = _suffix(src)
+    g = g.contiguous()
+    y, fwd = g, None
+    if method in ("monotonic", "monotonic-0"):
+        gf_ptr = _ptr(g_src)  # not linear in f: the knot kernel differentiates with respect to f as well
+    else:
+        wbytes = lib.ipx_slopes_vjp_workspace_bytes(code, n, outer, inner, g.element_size())
+        ws = torch.empty(max(int(wbytes), 16), dtype=torch.uint8, device=g.device)
+        L.check(getattr(lib, f"ipx_slopes_vjp_{suf}")(_ptr(x), n, _ptr(g), outer, inner, code, C.byref(opts), 1,
+                                                      _ptr(g_src), _ptr(ws), _stream()), "ipx_slopes_vjp")
+        gf_ptr = None
+        if method == "cubic2":
+            # T^-T g, left in the workspace behind the 3 n factor entries
+            es = g.element_size()
+            y = ws[3 * n * es: (3 * n + g.numel()) * es].view(g.dtype)
+            fwd = slopes
+    L.check(getattr(lib, f"ipx_slopes_knots_vjp_{suf}")(_ptr(x), n, _ptr(src), _ptr(fwd), _ptr(y), outer, inner,
+                                                        code, C.byref(opts), _ptr(g_x), gf_ptr, _stream()),
+            "ipx_slopes_knots_vjp")
+
+
+def _vjp_knots_chain(qs, knots, f, cotangent, method, derivative, extrap, period, functional, kwargs):
+    """vjp_knots for the methods evaluated from tables: the evaluation's own knot dependence
+    (ipx_vjp_knots_tables_*), the table cotangents (ipx_vjp_tables_*) and every link of the slope
+    chain in reverse (ipx_slopes_vjp_* / ipx_slopes_knots_vjp_*)."""
+    ndim = len(knots)
+    errorif(ndim not in (1, 2, 3) or len(qs) != ndim, ValueError, "need 1, 2 or 3 query and knot arrays")
+    methods = (METHODS_1D, METHODS_2D, METHODS_3D)[ndim - 1]
+    errorif(method not in methods, ValueError, f"unknown method {method}")
+    fshape = _shape(f)
+    _check_shapes(ndim, knots, fshape)
+    errorif(len(fshape) != ndim, NotImplementedError, "scalar-valued f only")
+    io = _Inputs(qs, knots, cotangent)
+    errorif(io.complex, NotImplementedError, "real data only")
+    kn = [io.coords(k) for k in knots]
+    qd, qshape, _ = io.queries(qs)
+    qd = [q.to(io.dev) for q in qd]
+    ft = _to_dev(f, io.rdt, io.dev).contiguous()
+    cot = _to_dev(cotangent, io.rdt, io.dev).reshape(-1)
+    errorif(cot.numel() != qd[0].numel(), ValueError, "cotangent must have the shape of the output")
+    periods = _parse_ndarg(period, ndim)
+    params = _make_params(ndim, _parse_ndarg(derivative, ndim), _parse_extrap(extrap, ndim), periods)
+    names = TABLES[ndim]
+    pk = [None] * ndim
+    mask, perms, kuse, sk = 0, [None] * ndim, list(kn), list(kn)
+    tabs = {"f": ft}
+    for ax in range(ndim):
+        if periods[ax] is None:
+            continue
+        pk[ax] = _periodic_knots_dev(kn[ax], periods[ax])
+        kuse[ax] = pk[ax][0]
+        if functional:  # slopes on the padded tables and knots (_spline.py:924-938 then :1027-1040)
+            tabs["f"] = _pad_periodic_dev(tabs["f"], ax, pk[ax][1])
+            sk[ax] = pk[ax][0]
+            mask |= L.IPX_WRAP_ONLY(ax)
+        else:
+            perms[ax] = pk[ax][1]
+            mask |= L.IPX_PERIODIC(ax)
+    for name, src, ax in CHAIN[ndim]:
+        tabs[name] = _slopes_dev(sk[ax], tabs[src], method, ax, kwargs)
+    tables = [tabs[n] for n in names]
+    pshape = list(tabs["f"].shape)
+    narr = (C.c_int32 * ndim)(*[int(pshape[ax]) for ax in range(ndim)])
+    lib = L.load()
+    suf = _suffix(ft)
+    # table cotangents
+    g = {n: torch.zeros_like(tabs["f"]) for n in names}
+    L.check(getattr(lib, f"ipx_vjp_tables_{suf}")(ndim, _ptr_array(qd), qd[0].numel(), _ptr_array(kuse),
+                                                  _ptr_array(perms), narr, 1, L.IPX_CUBIC, mask, C.byref(params), 0,
+                                                  _ptr(cot), _ptr_array([g[n] for n in names]), _stream()),
+            "ipx_vjp_tables")
+    # the evaluation's own dependence on the (lookup) knots
+    g_look = [torch.zeros_like(k) for k in kuse]
+    L.check(getattr(lib, f"ipx_vjp_knots_tables_{suf}")(ndim, _ptr_array(qd), qd[0].numel(), _ptr_array(kuse),
+                                                        _ptr_array(perms), narr, _ptr_array(tables), mask,
+                                                        C.byref(params), 0, _ptr(cot), _ptr_array(g_look), _stream()),
+            "ipx_vjp_knots_tables")
+    # the chain, last link first
+    g_sk = [torch.zeros_like(k) for k in sk]
+    for name, src, ax in reversed(CHAIN[ndim]):
+        _link_vjp(sk[ax], tabs[src], tabs[name], g[name], method, ax, kwargs, g[src], g_sk[ax])
+    gf = g["f"]
+    gk = []
+    for ax in range(ndim):
+        if pk[ax] is None:
+            gk.append(g_look[ax] + g_sk[ax])
+            continue
+        # padded knot u is the caller's knot perm[(u-1) mod n], shifted by a multiple of the period
+        n = fshape[ax]
+        src_ix = pk[ax][1].to(torch.int64)[(torch.arange(n + 2, device=io.dev) - 1) % n]
+        if functional:
+            gx = torch.zeros_like(kn[ax]).index_add_(0, src_ix, g_look[ax] + g_sk[ax])
+            shape = list(gf.shape)
+            shape[ax] = n
+            gf = torch.zeros(shape, dtype=gf.dtype, device=gf.device).index_add_(ax, src_ix, gf)
+        else:
+            gx = torch.zeros_like(kn[ax]).index_add_(0, src_ix, g_look[ax]) + g_sk[ax]
+        gk.append(gx)
+    out = dict(zip("xyz", gk))
+    out["f"] = gf
+    return out if io.want_torch else {k: v.cpu().numpy() for k, v in out.items()}
+
+
 def vjp_knots(qs, knots, f, cotangent, method="cubic", derivative=0, extrap=False, period=None,
               functional=True, **kwargs):
     """Reverse-mode rule of ``interp{1,2,3}d(q, knots, f, method)`` / ``Interpolator{1,2,3}D(knots, f,
@@ -1088,7 +1209,11 @@ def vjp_knots(qs, knots, f, cotangent, method="cubic", derivative=0, extrap=Fals
     (tests/test_interpolate.py:542-637).  ``cotangent`` has the shape of the output.  Returns
     ``{"x": ..., ["y", "z",] "f": ...}``.  ``functional``: which of the reference's two periodic
     conventions (slopes on the padded knots, or -- the classes -- on the original ones).
-    method = cubic, cardinal, catmull-rom."""
+    method = cubic, cardinal, catmull-rom (one kernel: per-query dual numbers over the local knots),
+    cubic2 and monotonic (chained: table cotangents, then every link of the slope chain in reverse --
+    a transposed tridiagonal solve per cubic2 link)."""
+    if method in _CHAIN_KNOT_METHODS:
+        return _vjp_knots_chain(qs, knots, f, cotangent, method, derivative, extrap, period, functional, kwargs)
     io, ndim, qd, qshape, kn, kuse, perms, ft, params, mask, code, c, narr = _grad_stencil_setup(
         qs, knots, f, method, derivative, extrap, period, functional, kwargs, cotangent)
     cot = _to_dev(cotangent, io.rdt, io.dev).reshape(-1)

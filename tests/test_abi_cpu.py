@@ -35,6 +35,9 @@ def header_symbols():
     for t in ("f32", "f64"):
         out.add(f"ipx_vjp_stencil_{t}")
         out.add(f"ipx_jvp_stencil_{t}")
+        # (IPX_DECL_GRAD_TABLES)
+        out.add(f"ipx_vjp_knots_tables_{t}")
+        out.add(f"ipx_slopes_knots_vjp_{t}")
     return {n for n in out if not n.startswith("ipx_eval") or re.fullmatch(r"ipx_eval([123]d|_stencil)_f(32|64)", n)}
 
 

@@ -274,3 +274,123 @@ def test_vjp_f_batched_tables():
     for b in range(3):
         gb = ipx.vjp_f(qs, (x, y), (10, 12), cot[:, b], "cubic2")
         np.testing.assert_allclose(g[..., b], gb, rtol=1e-12, atol=1e-13)
+
+
+def rev_jacobian(qs, knots, f, method, functional, **kw):
+    """d out[q] / d knots[ax][k] by reverse mode, one unit cotangent per query."""
+    nq = len(qs[0])
+    rev = [np.zeros((nq, len(k))) for k in knots]
+    for q in range(nq):
+        cot = np.zeros(nq)
+        cot[q] = 1.0
+        g = ipx.vjp_knots(qs, knots, f, cot, method, functional=functional, **kw)
+        for ax in range(len(knots)):
+            rev[ax][q] = g["xyz"[ax]]
+    return rev
+
+
+@pytest.mark.parametrize("method", ["cubic2", "monotonic"])
+def test_reference_test_ad_interp1d_chained_methods(method):
+    """tests/test_interpolate.py:543-569 for the two methods of its list that are evaluated from
+    tables: the reverse-mode Jacobian with respect to the knots against central differences of the
+    oracle, functional and class form (which coincide without a period, as the reference asserts)."""
+    xp = np.linspace(0, 2 * np.pi, 10)
+    x = np.linspace(0, 2 * np.pi, 20)
+    fp = np.sin(xp)
+    revs = []
+    for functional in (True, False):
+        rev = rev_jacobian((x,), (xp,), fp, method, functional)[0]
+        ofun = (lambda k: O.interp1d(x, k[0], fp, method)) if functional else (
+            lambda k: O.Interpolator1D(k[0], fp, method)(x))
+        jd = fd_knots(ofun, (xp,), 0)
+        np.testing.assert_allclose(rev[1:-1], jd[1:-1], rtol=1e-6, atol=1e-6)
+        revs.append(rev)
+    np.testing.assert_allclose(revs[0], revs[1], rtol=1e-14, atol=1e-14)
+
+
+def test_reference_test_ad_interp2d_3d_cubic2():
+    """tests/test_interpolate.py:571-637 for method cubic2: Jacobian with respect to the knot vectors."""
+    xp, yp = np.linspace(0, 4 * np.pi, 20), np.linspace(0, 2 * np.pi, 20)
+    x = y = np.linspace(0, 2 * np.pi, 30)
+    xxp, yyp = np.meshgrid(xp, yp, indexing="ij")
+    fp = np.sin(xxp) * np.cos(yyp)
+    rev = rev_jacobian((x, y), (xp, yp), fp, "cubic2", True)
+    jd = fd_knots(lambda k: O.interp2d(x, y, k[0], k[1], fp, "cubic2"), (xp, yp), 0)
+    np.testing.assert_allclose(rev[0][1:-1], jd[1:-1], rtol=1e-6, atol=1e-6)
+    xp, yp, zp = np.linspace(0, np.pi, 10), np.linspace(0, 2 * np.pi, 15), np.linspace(0, 1, 12)
+    x, y, z = np.linspace(0, np.pi, 13), np.linspace(0, 2 * np.pi, 13), np.linspace(0, 1, 13)
+    xxp, yyp, zzp = np.meshgrid(xp, yp, zp, indexing="ij")
+    fp = np.sin(xxp) * np.cos(yyp) * zzp**2
+    for functional in (True, False):
+        rev = rev_jacobian((x, y, z), (xp, yp, zp), fp, "cubic2", functional)
+        ofun = (lambda k: O.interp3d(x, y, z, *k, fp, "cubic2")) if functional else (
+            lambda k: O.Interpolator3D(*k, fp, "cubic2")(x, y, z))
+        for ax in range(3):
+            jd = fd_knots(ofun, (xp, yp, zp), ax)
+            np.testing.assert_allclose(rev[ax][1:-1], jd[1:-1], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("ndim", [1, 2, 3])
+def test_chained_knot_and_table_gradients_general(ndim):
+    """cubic2 (every boundary-condition kind, boundary values included) and monotonic on non-uniform
+    knots, periodic axes in both conventions, derivative orders, fills: the reverse rule against a
+    directional central difference of the oracle along random knot and table perturbations."""
+    rng = np.random.default_rng(900 + ndim)
+    ns = [9, 7, 8][:ndim]
+    nq = 300
+    for trial in range(10):
+        functional = trial % 2 == 0
+        method = ["cubic2", "monotonic", "cubic2", "monotonic-0", "cubic2"][trial % 5]
+        kw = {}
+        knots = [np.sort(rng.uniform(0.05, 2.0, n)) for n in ns]
+        for k in knots:
+            k[0] = 0.05
+        # (smooth data: monotonic switches branches where secants change sign)
+        f = rng.normal(size=ns) if method == "cubic2" else np.cumsum(rng.uniform(0.2, 1.0, size=ns), axis=0)
+        if method == "cubic2":
+            bcs = ["not-a-knot", "natural", ("clamped", "not-a-knot"), None, "not-a-knot"]
+            bc = bcs[(trial // 2) % 5]
+            if bc is None:
+                vshape0 = tuple(ns[1:])  # the chain's first link runs along axis 0 only in 1-D
+                bc = ((1, rng.normal(size=vshape0)), (2, rng.normal(size=vshape0))) if ndim == 1 else "natural"
+            kw["bc_type"] = bc
+        per_axes = [bool((trial >> 1) & 1) and ax != ndim - 1 for ax in range(ndim)] if ndim > 1 else [trial % 4 >= 2]
+        if method != "cubic2" and any(per_axes):
+            per_axes = [False] * ndim  # monotone data is not periodic
+        period = tuple(2.3 if p else None for p in per_axes)
+        period = period[0] if ndim == 1 else period
+        deriv = tuple(int(v) for v in rng.integers(0, 3, ndim)) if trial % 3 == 1 else (0,) * ndim
+        dfun = deriv[0] if ndim == 1 else deriv
+        extrap = [True, (True, 0.5), False][trial % 3]
+        qs = [rng.uniform(-0.3, 2.4, nq) for _ in range(ndim)]
+        what = f"nd={ndim} {method} functional={functional} per={period} d={deriv} ex={extrap} {list(kw)}"
+        if functional:
+            ofun = lambda k, ff: OFUN[ndim - 1](*qs, *k, ff, method, dfun, extrap, period, **kw)
+        else:
+            ofun = lambda k, ff: OCLS[ndim - 1](*k, ff, method, extrap, period, **kw)(*qs, *deriv)
+        with np.errstate(all="ignore"):
+            base = ofun(knots, f)
+        ok = np.isfinite(base)
+        kd = [rng.normal(size=n) for n in ns]
+        fd = rng.normal(size=ns)
+        h = 1e-6
+        kp = [k + h * d for k, d in zip(knots, kd)]
+        km = [k - h * d for k, d in zip(knots, kd)]
+        with np.errstate(all="ignore"):
+            num = (ofun(kp, f + h * fd) - ofun(km, f - h * fd)) / (2 * h)
+        smooth = ok & np.isfinite(num)
+        for ax in range(ndim):
+            P = period if ndim == 1 else period[ax]
+            for kk in (kp, km, knots):
+                kv, qv = (np.sort(np.mod(kk[ax], P)), np.mod(qs[ax], P)) if P is not None else (kk[ax], qs[ax])
+                cell = np.searchsorted(kv, qv, side="right")
+                if kk is kp:
+                    ref_cell = cell
+                smooth &= cell == ref_cell
+        cot = rng.normal(size=nq)
+        cot[~smooth] = 0.0
+        g = ipx.vjp_knots(qs, knots, f, cot, method, dfun, extrap, period, functional=functional, **kw)
+        lhs = float(np.dot(cot[smooth], num[smooth]))
+        rhs = sum(float(np.dot(g["xyz"[ax]], kd[ax])) for ax in range(ndim)) + float(np.sum(g["f"] * fd))
+        scale = max(1.0, float(np.abs(cot[smooth] * num[smooth]).sum()))
+        assert abs(lhs - rhs) <= 2e-5 * scale, (what, lhs, rhs)
