@@ -422,7 +422,27 @@ IPX_DECL_GRAD(f64, double)
  *   leaves in its workspace at element offset 3 n -- and `slopes` must hold the forward result of
  *   the link (NULL otherwise).  opts as in the forward call (boundary values included).  n >= 3.
  * --------------------------------------------------------------------------------- */
+/* Forward mode of the same pieces (jax.jacfwd in the reference's TestAD):
+ * ipx_jvp_knots_tables_*: tangent[q] = sum_k knots_dot[ax][k] * d out[q] / d knots[ax][k], tables fixed
+ *   (knots_dot over the lookup knots, entries may be NULL); the tangent of the tables is added by an
+ *   ordinary ipx_eval*d_* call on the tangent tables (the evaluation is linear in them).
+ * ipx_slopes_jvp_rows_*: directional derivative of every row of one link along (x_dot, f_dot) (either may
+ *   be NULL): the tangent of the slopes for cubic / cardinal / monotonic; for IPX_SLOPE_CUBIC2 the
+ *   right-hand side b' - T' s of the tangent system, which ipx_cubic2_solve_* then solves in place:
+ * ipx_cubic2_solve_*: y <- T(x)^-1 y for the spline matrix of _fd_derivs.py:199-286 (boundary KINDS
+ *   IPX_BC_*), Thomas without pivoting along the middle axis of the (outer, n, inner) view; workspace:
+ *   ipx_slopes_workspace_bytes(IPX_SLOPE_CUBIC2, n, sizeof(T)). */
 #define IPX_DECL_GRAD_TABLES(SUF, T)                                                                      \
+  int ipx_jvp_knots_tables_##SUF(int32_t ndim, const T* const* q, int64_t nq, const T* const* knots,      \
+                                 const int32_t* const* perm, const int32_t* n, const T* const* tables,    \
+                                 int32_t periodic_mask, const ipx_params* params,                         \
+                                 int32_t params_on_device, const T* const* knots_dot, T* tangent,         \
+                                 void* stream);                                                           \
+  int ipx_slopes_jvp_rows_##SUF(const T* x, int32_t n, const T* f, const T* slopes, const T* x_dot,       \
+                                const T* f_dot, int64_t outer, int64_t inner, int32_t method,             \
+                                const ipx_slope_opts* opts, T* out, void* stream);                        \
+  int ipx_cubic2_solve_##SUF(const T* x, int32_t n, int32_t bc_start, int32_t bc_end, T* y,               \
+                             int64_t outer, int64_t inner, void* workspace, void* stream);                \
   int ipx_vjp_knots_tables_##SUF(int32_t ndim, const T* const* q, int64_t nq, const T* const* knots,      \
                                  const int32_t* const* perm, const int32_t* n, const T* const* tables,    \
                                  int32_t periodic_mask, const ipx_params* params,                         \

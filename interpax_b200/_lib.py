@@ -69,7 +69,7 @@ SYMBOLS = (
     + [
         f"ipx_{name}_{t}"
         for name in ("bin_index", "slopes", "slopes_vjp", "slopes_pack", "periodic_knots", "pad_periodic", "pack", "cell_order", "cell_sort", "gather", "halo_table", "eval_stencil",
-                     "gather_multi", "scatter", "vjp_tables", "vjp_stencil", "jvp_stencil", "vjp_knots_tables", "slopes_knots_vjp", "ppoly_eval", "ppoly_pack", "ppoly_from_hermite",
+                     "gather_multi", "scatter", "vjp_tables", "vjp_stencil", "jvp_stencil", "vjp_knots_tables", "slopes_knots_vjp", "jvp_knots_tables", "slopes_jvp_rows", "cubic2_solve", "ppoly_eval", "ppoly_pack", "ppoly_from_hermite",
                      "ppoly_derivative", "ppoly_antiderivative")
         for t in ("f32", "f64")
     ]
@@ -135,6 +135,16 @@ def _declare(lib: C.CDLL) -> None:
         f.restype = C.c_int
         f.argtypes = [i32, C.POINTER(vp), i64, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.POINTER(vp), i32,
                       C.POINTER(Params), i32, vp, C.POINTER(vp), vp]
+        f = getattr(lib, f"ipx_jvp_knots_tables_{t}")
+        f.restype = C.c_int
+        f.argtypes = [i32, C.POINTER(vp), i64, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.POINTER(vp), i32,
+                      C.POINTER(Params), i32, C.POINTER(vp), vp, vp]
+        f = getattr(lib, f"ipx_slopes_jvp_rows_{t}")
+        f.restype = C.c_int
+        f.argtypes = [vp, i32, vp, vp, vp, vp, i64, i64, i32, C.POINTER(SlopeOpts), vp, vp]
+        f = getattr(lib, f"ipx_cubic2_solve_{t}")
+        f.restype = C.c_int
+        f.argtypes = [vp, i32, i32, i32, vp, i64, i64, vp, vp]
         f = getattr(lib, f"ipx_slopes_knots_vjp_{t}")
         f.restype = C.c_int
         f.argtypes = [vp, i32, vp, vp, vp, i64, i64, i32, C.POINTER(SlopeOpts), vp, vp, vp]

@@ -1123,41 +1123,12 @@ def _vjp_knots_chain(qs, knots, f, cotangent, method, derivative, extrap, period
     """vjp_knots for the methods evaluated from tables: the evaluation's own knot dependence
     (ipx_vjp_knots_tables_*), the table cotangents (ipx_vjp_tables_*) and every link of the slope
     chain in reverse (ipx_slopes_vjp_* / ipx_slopes_knots_vjp_*)."""
-    ndim = len(knots)
-    errorif(ndim not in (1, 2, 3) or len(qs) != ndim, ValueError, "need 1, 2 or 3 query and knot arrays")
-    methods = (METHODS_1D, METHODS_2D, METHODS_3D)[ndim - 1]
-    errorif(method not in methods, ValueError, f"unknown method {method}")
-    fshape = _shape(f)
-    _check_shapes(ndim, knots, fshape)
-    errorif(len(fshape) != ndim, NotImplementedError, "scalar-valued f only")
-    io = _Inputs(qs, knots, cotangent)
-    errorif(io.complex, NotImplementedError, "real data only")
-    kn = [io.coords(k) for k in knots]
-    qd, qshape, _ = io.queries(qs)
-    qd = [q.to(io.dev) for q in qd]
-    ft = _to_dev(f, io.rdt, io.dev).contiguous()
+    io, ndim, fshape, kn, qd, qshape, params, pk, mask, perms, kuse, sk, tabs = _chain_setup(
+        qs, knots, f, cotangent, method, derivative, extrap, period, functional, kwargs)
+    ft = tabs["f"]
     cot = _to_dev(cotangent, io.rdt, io.dev).reshape(-1)
     errorif(cot.numel() != qd[0].numel(), ValueError, "cotangent must have the shape of the output")
-    periods = _parse_ndarg(period, ndim)
-    params = _make_params(ndim, _parse_ndarg(derivative, ndim), _parse_extrap(extrap, ndim), periods)
     names = TABLES[ndim]
-    pk = [None] * ndim
-    mask, perms, kuse, sk = 0, [None] * ndim, list(kn), list(kn)
-    tabs = {"f": ft}
-    for ax in range(ndim):
-        if periods[ax] is None:
-            continue
-        pk[ax] = _periodic_knots_dev(kn[ax], periods[ax])
-        kuse[ax] = pk[ax][0]
-        if functional:  # slopes on the padded tables and knots (_spline.py:924-938 then :1027-1040)
-            tabs["f"] = _pad_periodic_dev(tabs["f"], ax, pk[ax][1])
-            sk[ax] = pk[ax][0]
-            mask |= L.IPX_WRAP_ONLY(ax)
-        else:
-            perms[ax] = pk[ax][1]
-            mask |= L.IPX_PERIODIC(ax)
-    for name, src, ax in CHAIN[ndim]:
-        tabs[name] = _slopes_dev(sk[ax], tabs[src], method, ax, kwargs)
     tables = [tabs[n] for n in names]
     pshape = list(tabs["f"].shape)
     narr = (C.c_int32 * ndim)(*[int(pshape[ax]) for ax in range(ndim)])
@@ -1201,6 +1172,102 @@ def _vjp_knots_chain(qs, knots, f, cotangent, method, derivative, extrap, period
     return out if io.want_torch else {k: v.cpu().numpy() for k, v in out.items()}
 
 
+def _chain_setup(qs, knots, f, dtype_item, method, derivative, extrap, period, functional, kwargs):
+    """Forward pass shared by the chained reverse and forward rules: tables of the slope chain."""
+    ndim = len(knots)
+    errorif(ndim not in (1, 2, 3) or len(qs) != ndim, ValueError, "need 1, 2 or 3 query and knot arrays")
+    methods = (METHODS_1D, METHODS_2D, METHODS_3D)[ndim - 1]
+    errorif(method not in methods, ValueError, f"unknown method {method}")
+    fshape = _shape(f)
+    _check_shapes(ndim, knots, fshape)
+    errorif(len(fshape) != ndim, NotImplementedError, "scalar-valued f only")
+    io = _Inputs(qs, knots, dtype_item)
+    errorif(io.complex, NotImplementedError, "real data only")
+    kn = [io.coords(k) for k in knots]
+    qd, qshape, _ = io.queries(qs)
+    qd = [q.to(io.dev) for q in qd]
+    ft = _to_dev(f, io.rdt, io.dev).contiguous()
+    periods = _parse_ndarg(period, ndim)
+    ex = _parse_extrap(extrap, ndim)
+    params = _make_params(ndim, _parse_ndarg(derivative, ndim), ex, periods)
+    pk = [None] * ndim
+    mask, perms, kuse, sk = 0, [None] * ndim, list(kn), list(kn)
+    tabs = {"f": ft}
+    for ax in range(ndim):
+        if periods[ax] is None:
+            continue
+        pk[ax] = _periodic_knots_dev(kn[ax], periods[ax])
+        kuse[ax] = pk[ax][0]
+        if functional:  # slopes on the padded tables and knots (_spline.py:924-938 then :1027-1040)
+            tabs["f"] = _pad_periodic_dev(tabs["f"], ax, pk[ax][1])
+            sk[ax] = pk[ax][0]
+            mask |= L.IPX_WRAP_ONLY(ax)
+        else:
+            perms[ax] = pk[ax][1]
+            mask |= L.IPX_PERIODIC(ax)
+    for name, src, ax in CHAIN[ndim]:
+        tabs[name] = _slopes_dev(sk[ax], tabs[src], method, ax, kwargs)
+    return io, ndim, fshape, kn, qd, qshape, params, pk, mask, perms, kuse, sk, tabs
+
+
+def _jvp_knots_chain(qs, knots, f, knots_dot, f_dot, method, derivative, extrap, period, functional, kwargs):
+    """jvp_knots for the methods evaluated from tables (forward mode of _vjp_knots_chain)."""
+    io, ndim, fshape, kn, qd, qshape, params, pk, mask, perms, kuse, sk, tabs = _chain_setup(
+        qs, knots, f, f, method, derivative, extrap, period, functional, kwargs)
+    names = TABLES[ndim]
+    lib = L.load()
+    suf = _suffix(tabs["f"])
+    kd = [None if v is None else _to_dev(v, io.rdt, io.dev).reshape(-1).contiguous() for v in knots_dot]
+    # tangents of the lookup knots and of the knots the slopes are taken on
+    kd_look, kd_sk = list(kd), list(kd)
+    tf = None if f_dot is None else _to_dev(f_dot, io.rdt, io.dev).contiguous()
+    for ax in range(ndim):
+        if pk[ax] is None:
+            continue
+        n = fshape[ax]
+        src_ix = pk[ax][1].to(torch.int64)[(torch.arange(n + 2, device=io.dev) - 1) % n]
+        kd_look[ax] = None if kd[ax] is None else kd[ax][src_ix].contiguous()
+        if functional:
+            kd_sk[ax] = kd_look[ax]
+            if tf is not None:
+                tf = _pad_periodic_dev(tf, ax, pk[ax][1])
+    tt = {"f": tf if tf is not None else torch.zeros_like(tabs["f"])}
+    for name, src, ax in CHAIN[ndim]:
+        x = sk[ax]
+        n = x.shape[0]
+        outer = int(np.prod(tabs[src].shape[:ax], dtype=np.int64))
+        inner = int(np.prod(tabs[src].shape[ax + 1:], dtype=np.int64))
+        opts, keep = _slope_opts_values(tabs[src], method, ax, kwargs)
+        out = torch.empty_like(tabs[src])
+        code = _SLOPE_CODE[method]
+        L.check(getattr(lib, f"ipx_slopes_jvp_rows_{suf}")(
+            _ptr(x), n, _ptr(tabs[src]), _ptr(tabs[name]) if method == "cubic2" else None, _ptr(kd_sk[ax]),
+            _ptr(tt[src]), outer, inner, code, C.byref(opts), _ptr(out), _stream()), "ipx_slopes_jvp_rows")
+        if method == "cubic2":
+            ws = torch.empty(max(int(lib.ipx_slopes_workspace_bytes(code, n, out.element_size())), 16),
+                             dtype=torch.uint8, device=out.device)
+            L.check(getattr(lib, f"ipx_cubic2_solve_{suf}")(_ptr(x), n, opts.bc_start, opts.bc_end, _ptr(out), outer,
+                                                            inner, _ptr(ws), _stream()), "ipx_cubic2_solve")
+        tt[name] = out
+    pshape = list(tabs["f"].shape)
+    narr = (C.c_int32 * ndim)(*[int(pshape[ax]) for ax in range(ndim)])
+    tan = torch.empty(qd[0].numel(), dtype=io.tdt, device=io.dev)
+    L.check(getattr(lib, f"ipx_jvp_knots_tables_{suf}")(
+        ndim, _ptr_array(qd), qd[0].numel(), _ptr_array(kuse), _ptr_array(perms), narr,
+        _ptr_array([tabs[n] for n in names]), mask, C.byref(params), 0, _ptr_array(kd_look), _ptr(tan), _stream()),
+        "ipx_jvp_knots_tables")
+    # the evaluation is linear in the tables: its tangent is the evaluation of the tangent tables, with
+    # every extrapolation fill (a constant) replaced by zero
+    zp = L.Params()
+    for ax in range(ndim):
+        a, b = params.axis[ax], zp.axis[ax]
+        b.derivative, b.keep_lo, b.keep_hi, b.period = a.derivative, a.keep_lo, a.keep_hi, a.period
+        b.fill_lo = b.fill_hi = 0.0
+    lin, _ = _eval_dev(ndim, qd, kuse, perms, pshape, [tt[n] for n in names], L.IPX_SOA, 1, L.IPX_CUBIC, mask, zp)
+    tan = (tan + lin.reshape(-1)).reshape(qshape)
+    return tan if io.want_torch else tan.cpu().numpy()
+
+
 def vjp_knots(qs, knots, f, cotangent, method="cubic", derivative=0, extrap=False, period=None,
               functional=True, **kwargs):
     """Reverse-mode rule of ``interp{1,2,3}d(q, knots, f, method)`` / ``Interpolator{1,2,3}D(knots, f,
@@ -1233,6 +1300,9 @@ def jvp_knots(qs, knots, f, knots_dot, f_dot=None, method="cubic", derivative=0,
               functional=True, **kwargs):
     """Forward-mode rule of the same map: the tangent of the output for tangents ``knots_dot``
     (a tuple, entries may be None) and ``f_dot`` (or None)."""
+    if method in _CHAIN_KNOT_METHODS:
+        return _jvp_knots_chain(qs, knots, f, knots_dot, f_dot, method, derivative, extrap, period, functional,
+                                kwargs)
     io, ndim, qd, qshape, kn, kuse, perms, ft, params, mask, code, c, narr = _grad_stencil_setup(
         qs, knots, f, method, derivative, extrap, period, functional, kwargs, f)
     kd = [None if v is None else _to_dev(v, io.rdt, io.dev).reshape(-1) for v in knots_dot]

@@ -96,8 +96,11 @@ __device__ __forceinline__ void gt_atomic_add(double* p, double v) { atomicAdd(p
 template <typename T, int ND> struct KtArgs {
   AxisDesc<T> ax[ND];
   const T* __restrict__ tab[1 << ND];  // reference stacking order, scalar-valued
-  const T* __restrict__ cot;           // (nq)
-  T* __restrict__ grad_knots[ND];      // nk entries each (lookup knots), or NULL
+  const T* __restrict__ cot;           // reverse mode: (nq)
+  T* __restrict__ grad_knots[ND];      // reverse mode: nk entries each (lookup knots), or NULL
+  const T* __restrict__ knots_dot[ND]; // forward mode: nk entries each, or NULL
+  T* __restrict__ tangent;             // forward mode: (nq), written
+  int32_t jvp;
   int64_t nq;
   ipx_params hp;
   const ipx_params* dp;
@@ -130,7 +133,10 @@ __global__ void __launch_bounds__(kGtThreads) vjp_knots_tables_kernel(const KtAr
         if (!P.axis[ax].keep_hi && L[ax].above) filled = true;
       }
     }
-    if (filled) continue;
+    if (filled) {
+      if (a.jvp) a.tangent[qi] = T(0);
+      continue;
+    }
     // hermite_weights in dual numbers over (x0, x1) of the cell
     D2 w[ND][4];
 #pragma unroll
@@ -183,6 +189,15 @@ __global__ void __launch_bounds__(kGtThreads) vjp_knots_tables_kernel(const KtAr
         }
       }
     }
+    if (a.jvp) {
+      T tan = T(0);
+#pragma unroll
+      for (int ax = 0; ax < ND; ++ax)
+        if (a.knots_dot[ax] != nullptr)
+          tan += g[ax][0] * a.knots_dot[ax][L[ax].i - 1] + g[ax][1] * a.knots_dot[ax][L[ax].i];
+      a.tangent[qi] = tan;
+      continue;
+    }
     const T cot = a.cot[qi];
 #pragma unroll
     for (int ax = 0; ax < ND; ++ax) {
@@ -196,11 +211,15 @@ __global__ void __launch_bounds__(kGtThreads) vjp_knots_tables_kernel(const KtAr
 template <typename T, int ND>
 static int launch_kt(const T* const* q, int64_t nq, const T* const* knots, const int32_t* const* perm,
                      const int32_t* n, const T* const* tables, int32_t periodic_mask, const ipx_params* params,
-                     int32_t params_on_device, const T* cot, T* const* grad_knots, void* stream) {
-  if (nq < 0 || params == nullptr || grad_knots == nullptr || tables == nullptr) return IPX_EINVAL;
+                     int32_t params_on_device, const T* cot, T* const* grad_knots, const T* const* knots_dot,
+                     T* tangent, void* stream) {
+  const int jvp = tangent != nullptr;
+  if (nq < 0 || params == nullptr || tables == nullptr) return IPX_EINVAL;
   if (nq == 0) return IPX_OK;
-  if (cot == nullptr) return IPX_EINVAL;
+  if (jvp ? knots_dot == nullptr : (cot == nullptr || grad_knots == nullptr)) return IPX_EINVAL;
   KtArgs<T, ND> a;
+  a.jvp = jvp;
+  a.tangent = tangent;
   for (int ax = 0; ax < ND; ++ax) {
     if (q[ax] == nullptr || knots[ax] == nullptr || n[ax] < 2) return IPX_EINVAL;
     const int per = (periodic_mask >> ax) & 1;
@@ -213,7 +232,8 @@ static int launch_kt(const T* const* q, int64_t nq, const T* const* knots, const
     a.ax[ax].nk = per ? n[ax] + 2 : n[ax];
     a.ax[ax].periodic = per;
     a.ax[ax].wrap = per | wrap_only;
-    a.grad_knots[ax] = grad_knots[ax];
+    a.grad_knots[ax] = jvp ? nullptr : grad_knots[ax];
+    a.knots_dot[ax] = jvp ? knots_dot[ax] : nullptr;
   }
   for (int k = 0; k < (1 << ND); ++k) {
     if (tables[k] == nullptr) return IPX_EINVAL;
@@ -234,11 +254,14 @@ static int launch_kt(const T* const* q, int64_t nq, const T* const* knots, const
 template <typename T>
 static int kt_dispatch(int32_t ndim, const T* const* q, int64_t nq, const T* const* knots, const int32_t* const* perm,
                        const int32_t* n, const T* const* tables, int32_t periodic_mask, const ipx_params* params,
-                       int32_t pod, const T* cot, T* const* grad_knots, void* stream) {
+                       int32_t pod, const T* cot, T* const* grad_knots, const T* const* knots_dot, T* tangent,
+                       void* stream) {
   if (ndim < 1 || ndim > 3 || q == nullptr || knots == nullptr || n == nullptr) return IPX_EINVAL;
-  if (ndim == 1) return launch_kt<T, 1>(q, nq, knots, perm, n, tables, periodic_mask, params, pod, cot, grad_knots, stream);
-  if (ndim == 2) return launch_kt<T, 2>(q, nq, knots, perm, n, tables, periodic_mask, params, pod, cot, grad_knots, stream);
-  return launch_kt<T, 3>(q, nq, knots, perm, n, tables, periodic_mask, params, pod, cot, grad_knots, stream);
+  if (ndim == 1)
+    return launch_kt<T, 1>(q, nq, knots, perm, n, tables, periodic_mask, params, pod, cot, grad_knots, knots_dot, tangent, stream);
+  if (ndim == 2)
+    return launch_kt<T, 2>(q, nq, knots, perm, n, tables, periodic_mask, params, pod, cot, grad_knots, knots_dot, tangent, stream);
+  return launch_kt<T, 3>(q, nq, knots, perm, n, tables, periodic_mask, params, pod, cot, grad_knots, knots_dot, tangent, stream);
 }
 
 // --------------------------------------------------------------------------- (2) slope links
@@ -259,9 +282,12 @@ template <typename T> struct SkArgs {
 // One row in dual numbers: seeds 0..2 = the three knots j0..j0+2, seeds 3..5 (N == 6) = the three
 // table values.  Returns the slope (local methods) or the residual of the cubic2 equation.
 template <typename T, int N>
+__device__ __forceinline__ DualN<T, N> sk_row_eval(const SkArgs<T>& a, const DualN<T, N> (&X)[3],
+                                                   const DualN<T, N> (&F)[3], int64_t base, int64_t col, int k, int j0);
+
+template <typename T, int N>
 __device__ __forceinline__ DualN<T, N> sk_row(const SkArgs<T>& a, int64_t base, int64_t col, int k, int j0) {
   using D = DualN<T, N>;
-  const int n = a.n;
   D X[3], F[3];
 #pragma unroll
   for (int m = 0; m < 3; ++m) {
@@ -270,6 +296,14 @@ __device__ __forceinline__ DualN<T, N> sk_row(const SkArgs<T>& a, int64_t base, 
     if constexpr (N == 6) F[m] = dn_seed<T, N>(fv, 3 + m);
     else F[m] = dn_const<T, N>(fv);
   }
+  return sk_row_eval<T, N>(a, X, F, base, col, k, j0);
+}
+
+template <typename T, int N>
+__device__ __forceinline__ DualN<T, N> sk_row_eval(const SkArgs<T>& a, const DualN<T, N> (&X)[3],
+                                                   const DualN<T, N> (&F)[3], int64_t base, int64_t col, int k, int j0) {
+  using D = DualN<T, N>;
+  const int n = a.n;
   const D h0 = X[1] - X[0], h1 = X[2] - X[1];
   const D s01 = dn_recip(h0) * (F[1] - F[0]), s12 = dn_recip(h1) * (F[2] - F[1]);
   const D zero = dn_const<T, N>(T(0));
@@ -364,6 +398,41 @@ __global__ void __launch_bounds__(kGtThreads) slopes_knots_vjp_kernel(const SkAr
   }
 }
 
+// forward mode of one link: the directional derivative of every row along (x_dot, f_dot) -- the
+// tangent of the slopes for the local methods, the right-hand side  b' - T' s  of the tangent system
+// for cubic2 (the caller solves T s' = rhs with ipx_cubic2_solve_*)
+template <typename T> struct SkFwdArgs {
+  SkArgs<T> a;
+  const T* __restrict__ x_dot;  // n entries or NULL
+  const T* __restrict__ f_dot;  // shape of f or NULL
+  T* __restrict__ out;          // shape of f
+};
+template <typename T>
+__global__ void __launch_bounds__(kGtThreads) slopes_jvp_rows_kernel(const SkFwdArgs<T> w) {
+  const SkArgs<T>& a = w.a;
+  const int64_t total = a.outer * a.n * a.inner;
+  const int64_t stride = (int64_t)gridDim.x * kGtThreads;
+  const int n = a.n;
+  using D = DualN<T, 1>;
+  for (int64_t e = (int64_t)blockIdx.x * kGtThreads + threadIdx.x; e < total; e += stride) {
+    const int64_t i = e % a.inner, rr = e / a.inner;
+    const int k = (int)(rr % n);
+    const int64_t o = rr / n;
+    const int64_t base = o * n * a.inner + i;
+    const int j0 = k == 0 ? 0 : (k == n - 1 ? n - 3 : k - 1);
+    D X[3], F[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      X[m].v = a.x[j0 + m];
+      X[m].d[0] = w.x_dot ? w.x_dot[j0 + m] : T(0);
+      const int64_t at = base + (int64_t)(j0 + m) * a.inner;
+      F[m].v = a.f[at];
+      F[m].d[0] = w.f_dot ? w.f_dot[at] : T(0);
+    }
+    w.out[e] = sk_row_eval<T, 1>(a, X, F, base, o * a.inner + i, k, j0).d[0];
+  }
+}
+
 // (cubic2: the caller passes y = T^-T g, which ipx_slopes_vjp_* leaves in its workspace)
 template <typename T>
 static int launch_sk(const T* x, int32_t n, const T* f, const T* s, const T* y, int64_t outer, int64_t inner,
@@ -413,6 +482,42 @@ static int launch_sk(const T* x, int32_t n, const T* f, const T* s, const T* y, 
 }
 }  // namespace ipx
 
+namespace ipx {
+template <typename T>
+static int launch_sk_fwd(const T* x, int32_t n, const T* f, const T* s, const T* x_dot, const T* f_dot, int64_t outer,
+                         int64_t inner, int32_t method, const ipx_slope_opts* opts, T* out, void* stream) {
+  if (outer < 0 || inner < 0 || n < 0) return IPX_EINVAL;
+  const int64_t total = outer * n * inner;
+  if (total == 0) return IPX_OK;
+  if (x == nullptr || f == nullptr || out == nullptr) return IPX_EINVAL;
+  if (n < 3) return IPX_EUNSUPPORTED;
+  SkFwdArgs<T> w{};
+  SkArgs<T>& a = w.a;
+  a.x = x; a.f = f; a.s = s;
+  a.outer = outer; a.inner = inner; a.n = n; a.method = method;
+  a.fac = T(1) - (opts ? T(opts->c) : T(0));
+  a.bs = opts ? opts->bc_start : IPX_BC_NOT_A_KNOT;
+  a.be = opts ? opts->bc_end : IPX_BC_NOT_A_KNOT;
+  a.v0 = opts ? static_cast<const T*>(opts->bc_start_value) : nullptr;
+  a.v1 = opts ? static_cast<const T*>(opts->bc_end_value) : nullptr;
+  w.x_dot = x_dot; w.f_dot = f_dot; w.out = out;
+  if (method == IPX_SLOPE_CUBIC2) {
+    if (s == nullptr || a.bs < 0 || a.bs > 2 || a.be < 0 || a.be > 2) return IPX_EINVAL;
+    if (n == 3 && a.bs == IPX_BC_NOT_A_KNOT && a.be == IPX_BC_NOT_A_KNOT) return IPX_EUNSUPPORTED;
+  } else if (method != IPX_SLOPE_CUBIC && method != IPX_SLOPE_CARDINAL && method != IPX_SLOPE_MONOTONIC &&
+             method != IPX_SLOPE_MONOTONIC0) {
+    return (method >= 0 && method <= IPX_SLOPE_AKIMA_COMPLEX) ? IPX_EUNSUPPORTED : IPX_EINVAL;
+  }
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t need = (total + kGtThreads - 1) / kGtThreads;
+  int64_t cap = (int64_t)sms * 16;
+  slopes_jvp_rows_kernel<T><<<(int)(need < cap ? need : cap), kGtThreads, 0, static_cast<cudaStream_t>(stream)>>>(w);
+  count_launches(1);
+  return cudaPeekAtLastError() == cudaSuccess ? IPX_OK : IPX_ELAUNCH;
+}
+}  // namespace ipx
+
 #define IPX_DEFINE_GT(SUF, T)                                                                                      \
   extern "C" int ipx_vjp_knots_tables_##SUF(int32_t ndim, const T* const* q, int64_t nq, const T* const* knots,    \
                                             const int32_t* const* perm, const int32_t* n, const T* const* tables,  \
@@ -420,7 +525,21 @@ static int launch_sk(const T* x, int32_t n, const T* f, const T* s, const T* y, 
                                             int32_t params_on_device, const T* cotangent, T* const* grad_knots,    \
                                             void* stream) {                                                        \
     return ipx::kt_dispatch<T>(ndim, q, nq, knots, perm, n, tables, periodic_mask, params, params_on_device,       \
-                               cotangent, grad_knots, stream);                                                     \
+                               cotangent, grad_knots, nullptr, nullptr, stream);                                   \
+  }                                                                                                                \
+  extern "C" int ipx_jvp_knots_tables_##SUF(int32_t ndim, const T* const* q, int64_t nq, const T* const* knots,    \
+                                            const int32_t* const* perm, const int32_t* n, const T* const* tables,  \
+                                            int32_t periodic_mask, const ipx_params* params,                       \
+                                            int32_t params_on_device, const T* const* knots_dot, T* tangent,       \
+                                            void* stream) {                                                        \
+    if (tangent == nullptr) return IPX_EINVAL;                                                                     \
+    return ipx::kt_dispatch<T>(ndim, q, nq, knots, perm, n, tables, periodic_mask, params, params_on_device,       \
+                               nullptr, nullptr, knots_dot, tangent, stream);                                      \
+  }                                                                                                                \
+  extern "C" int ipx_slopes_jvp_rows_##SUF(const T* x, int32_t n, const T* f, const T* slopes, const T* x_dot,     \
+                                           const T* f_dot, int64_t outer, int64_t inner, int32_t method,           \
+                                           const ipx_slope_opts* opts, T* out, void* stream) {                     \
+    return ipx::launch_sk_fwd<T>(x, n, f, slopes, x_dot, f_dot, outer, inner, method, opts, out, stream);          \
   }                                                                                                                \
   extern "C" int ipx_slopes_knots_vjp_##SUF(const T* x, int32_t n, const T* f, const T* slopes, const T* y,        \
                                             int64_t outer, int64_t inner, int32_t method,                          \

@@ -412,6 +412,33 @@ __global__ void cubic2_solve_kernel(const SlopeArgs<T> a, const BcArgs<T> bc,
   }
 }
 
+// T y = rhs for a given right-hand side (forward mode of the slopes with respect to the knots:
+// the tangent system has the same matrix), in place, one thread per column
+template <typename T>
+__global__ void cubic2_solve_rhs_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t outer, int64_t inner,
+                                        int n, int bs, int be, const T* __restrict__ ws) {
+  const int64_t cols = outer * inner;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; col < cols; col += stride) {
+    const int64_t o = col / inner, i = col - o * inner;
+    const int64_t base = o * n * inner + i;
+    T dprev = T(0);
+    for (int k = 0; k < n; ++k) {
+      T lo, di, up;
+      bool masked;
+      cubic2_row(x, n, bs, be, k, lo, di, up, masked);
+      const T rhs = masked ? T(0) : y[base + (int64_t)k * inner];
+      dprev = (rhs - lo * dprev) / ws[n + k];
+      y[base + (int64_t)k * inner] = dprev;
+    }
+    T xnext = T(0);
+    for (int k = n - 1; k >= 0; --k) {
+      xnext = y[base + (int64_t)k * inner] - ws[k] * xnext;
+      y[base + (int64_t)k * inner] = xnext;
+    }
+  }
+}
+
 // ---- long axes: windowed Thomas ------------------------------------------------------
 // The spline system is strictly diagonally dominant in its interior rows
 // (|lower| + |upper| = diag / 2 for any knot spacing), so the influence of a row on the
@@ -1207,6 +1234,24 @@ static int launch_slopes_vjp(const T* x, int32_t n, const T* g, int64_t outer, i
 }
 
 }  // namespace ipx
+
+#define IPX_DEFINE_C2SOLVE(SUF, T)                                                                              \
+  extern "C" int ipx_cubic2_solve_##SUF(const T* x, int32_t n, int32_t bc_start, int32_t bc_end, T* y,          \
+                                        int64_t outer, int64_t inner, void* workspace, void* stream) {           \
+    if (x == nullptr || y == nullptr || workspace == nullptr || n < 3 || outer < 0 || inner < 0)                \
+      return IPX_EINVAL;                                                                                         \
+    if (bc_start < 0 || bc_start > 2 || bc_end < 0 || bc_end > 2) return IPX_EINVAL;                            \
+    if (outer * inner == 0) return IPX_OK;                                                                       \
+    cudaStream_t s = static_cast<cudaStream_t>(stream);                                                          \
+    T* ws = static_cast<T*>(workspace);                                                                          \
+    ipx::cubic2_factor_kernel<T><<<1, 32, 0, s>>>(x, n, bc_start, bc_end, ws);                                   \
+    ipx::cubic2_solve_rhs_kernel<T><<<ipx::slope_grid(outer * inner), ipx::kSlopeThreads, 0, s>>>(               \
+        x, y, outer, inner, n, bc_start, bc_end, ws);                                                            \
+    ipx::count_launches(2);                                                                                      \
+    return cudaPeekAtLastError() == cudaSuccess ? IPX_OK : IPX_ELAUNCH;                                          \
+  }
+IPX_DEFINE_C2SOLVE(f32, float)
+IPX_DEFINE_C2SOLVE(f64, double)
 
 extern "C" size_t ipx_slopes_vjp_workspace_bytes(int32_t method, int32_t n, int64_t outer, int64_t inner,
                                                  int32_t elem_size) {

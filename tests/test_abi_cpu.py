@@ -38,6 +38,9 @@ def header_symbols():
         # (IPX_DECL_GRAD_TABLES)
         out.add(f"ipx_vjp_knots_tables_{t}")
         out.add(f"ipx_slopes_knots_vjp_{t}")
+        out.add(f"ipx_jvp_knots_tables_{t}")
+        out.add(f"ipx_slopes_jvp_rows_{t}")
+        out.add(f"ipx_cubic2_solve_{t}")
     return {n for n in out if not n.startswith("ipx_eval") or re.fullmatch(r"ipx_eval([123]d|_stencil)_f(32|64)", n)}
 
 

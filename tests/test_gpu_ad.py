@@ -394,3 +394,39 @@ def test_chained_knot_and_table_gradients_general(ndim):
         rhs = sum(float(np.dot(g["xyz"[ax]], kd[ax])) for ax in range(ndim)) + float(np.sum(g["f"] * fd))
         scale = max(1.0, float(np.abs(cot[smooth] * num[smooth]).sum()))
         assert abs(lhs - rhs) <= 2e-5 * scale, (what, lhs, rhs)
+
+
+@pytest.mark.parametrize("method", ["cubic2", "monotonic"])
+def test_chained_forward_mode_equals_reverse_mode(method):
+    """jacfwd == jacrev for the chained methods (tests/test_interpolate.py:564-566, 632-634), 1-D on
+    the reference's setup and 3-D with a periodic axis, plus f tangents through the transpose identity."""
+    xp = np.linspace(0, 2 * np.pi, 10)
+    x = np.linspace(0, 2 * np.pi, 20)
+    fp = np.sin(xp)
+    for functional in (True, False):
+        rev = rev_jacobian((x,), (xp,), fp, method, functional)[0]
+        fwd = np.zeros_like(rev)
+        for k in range(len(xp)):
+            dots = np.zeros(len(xp))
+            dots[k] = 1.0
+            fwd[:, k] = ipx.jvp_knots((x,), (xp,), fp, (dots,), None, method, functional=functional)
+        np.testing.assert_allclose(fwd, rev, rtol=1e-13, atol=1e-13)
+    rng = np.random.default_rng(4242)
+    ns = [8, 7, 9]
+    knots = [np.sort(rng.uniform(0.05, 2.0, n)) for n in ns]
+    f = rng.normal(size=ns) if method == "cubic2" else np.cumsum(rng.uniform(0.2, 1.0, size=ns), axis=0)
+    qs = [rng.uniform(-0.3, 2.4, 500) for _ in range(3)]
+    for functional in (True, False):
+        for period, extrap, deriv in (((None, None, None), (True, 0.5), (0, 0, 0)),
+                                      ((2.3, None, None), True, (1, 0, 2)) if method == "cubic2" else
+                                      ((None, None, None), False, (0, 1, 0))):
+            kw = {"bc_type": ("natural", "not-a-knot")} if method == "cubic2" else {}
+            cot = rng.normal(size=500)
+            kd = [rng.normal(size=n) for n in ns]
+            fd = rng.normal(size=ns)
+            g = ipx.vjp_knots(qs, knots, f, cot, method, deriv, extrap, period, functional=functional, **kw)
+            tan = ipx.jvp_knots(qs, knots, f, tuple(kd), fd, method, deriv, extrap, period, functional=functional, **kw)
+            assert np.all(np.isfinite(tan))
+            lhs = float(np.dot(cot, tan))
+            rhs = sum(float(np.dot(g["xyz"[ax]], kd[ax])) for ax in range(3)) + float(np.sum(g["f"] * fd))
+            assert abs(lhs - rhs) <= 1e-10 * max(1.0, abs(lhs)), (method, functional, period, lhs, rhs)
