@@ -584,7 +584,7 @@ def run_ours(args):
                                  "evaluation from f (table 8x smaller than the records)"},
         "random_order_presorted": {"value": total_q / (ms_presort * 1e-3), "ms_per_step": ms_presort,
                                    "note": "same random-order queries, Interpolator3D(..., presort=True): "
-                                           "cell-key radix sort + gather + evaluate + scatter, all timed"},
+                                           "cell-key radix sort, then one kernel that gathers the coordinates, evaluates and scatters the results; all timed"},
         "functional_form": {"value": total_q / (ms_fun * 1e-3), "ms_per_step": ms_fun,
                             "query_order": "cell-sorted",
                             "note": "interp3d(xq, yq, zq, x, y, z, f, 'cubic', ...): tables rebuilt from f inside "

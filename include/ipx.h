@@ -336,6 +336,33 @@ int ipx_cell_sort_f64(int32_t ndim, const double* const* q, int64_t nq, const do
                       const int32_t* n, int32_t periodic_mask, const ipx_params* params,
                       int32_t params_on_device, uint32_t* order, double* const* q_sorted,
                       void* workspace, void* stream);
+/* ipx_cell_order_records_*: ipx_cell_order_* plus the interleaved copy of the coordinates it sorts by,
+ * records[e * R + ax] = q[ax][e] with R = 1, 2, 4 for ndim = 1, 2, 3 (32-byte aligned, nq * R
+ * elements, written for the caller's use): what ipx_eval_stencil_perm_* reads, one sector per query.
+ * workspace: ipx_cell_order_workspace_bytes(nq). */
+int ipx_cell_order_records_f32(int32_t ndim, const float* const* q, int64_t nq, const float* const* knots,
+                               const int32_t* n, int32_t periodic_mask, const ipx_params* params,
+                               int32_t params_on_device, uint32_t* order, float* records, void* workspace,
+                               void* stream);
+int ipx_cell_order_records_f64(int32_t ndim, const double* const* q, int64_t nq, const double* const* knots,
+                               const int32_t* n, int32_t periodic_mask, const ipx_params* params,
+                               int32_t params_on_device, uint32_t* order, double* records, void* workspace,
+                               void* stream);
+/* ipx_eval_stencil_perm_*: ipx_eval_stencil_* visiting the queries in the order given --
+ * out[order[k]] = value at query order[k], k = 0 .. nq-1, coordinates read from coord_records -- i.e.
+ * scatter(eval(gather(q))) in ONE kernel: the pre-sorted call without its two permutation passes.
+ * Results are bit-identical to ipx_eval_stencil_* on the same queries.  q is still passed (argument
+ * checks only).  One query per lane (the sparse shape). */
+int ipx_eval_stencil_perm_f32(int32_t ndim, const float* const* q, int64_t nq, const float* const* knots,
+                              const float* const* slope_knots, const int32_t* n, const float* halo,
+                              int32_t slope_method, double c, int32_t periodic_mask, const ipx_params* params,
+                              int32_t params_on_device, const uint32_t* order, const float* coord_records,
+                              float* out, void* stream);
+int ipx_eval_stencil_perm_f64(int32_t ndim, const double* const* q, int64_t nq, const double* const* knots,
+                              const double* const* slope_knots, const int32_t* n, const double* halo,
+                              int32_t slope_method, double c, int32_t periodic_mask, const ipx_params* params,
+                              int32_t params_on_device, const uint32_t* order, const double* coord_records,
+                              double* out, void* stream);
 int ipx_gather_f32(const float* src, const uint32_t* order, int64_t n, int64_t batch, float* dst,
                    void* stream);
 int ipx_gather_f64(const double* src, const uint32_t* order, int64_t n, int64_t batch, double* dst,

@@ -68,7 +68,7 @@ SYMBOLS = (
     + [f"ipx_eval{d}d_{t}" for d in (1, 2, 3) for t in ("f32", "f64")]
     + [
         f"ipx_{name}_{t}"
-        for name in ("bin_index", "slopes", "slopes_vjp", "slopes_pack", "periodic_knots", "pad_periodic", "pack", "cell_order", "cell_sort", "gather", "halo_table", "eval_stencil",
+        for name in ("bin_index", "slopes", "slopes_vjp", "slopes_pack", "periodic_knots", "pad_periodic", "pack", "cell_order", "cell_sort", "cell_order_records", "eval_stencil_perm", "gather", "halo_table", "eval_stencil",
                      "gather_multi", "scatter", "vjp_tables", "vjp_stencil", "jvp_stencil", "vjp_knots_tables", "slopes_knots_vjp", "jvp_knots_tables", "slopes_jvp_rows", "cubic2_solve", "ppoly_eval", "ppoly_pack", "ppoly_from_hermite",
                      "ppoly_derivative", "ppoly_antiderivative")
         for t in ("f32", "f64")
@@ -167,6 +167,14 @@ def _declare(lib: C.CDLL) -> None:
         f.restype = C.c_int
         f.argtypes = [i32, C.POINTER(vp), i64, C.POINTER(vp), C.POINTER(i32), i32, C.POINTER(Params), i32,
                       vp, vp, vp]
+        f = getattr(lib, f"ipx_cell_order_records_{t}")
+        f.restype = C.c_int
+        f.argtypes = [i32, C.POINTER(vp), i64, C.POINTER(vp), C.POINTER(i32), i32, C.POINTER(Params), i32,
+                      vp, vp, vp, vp]
+        f = getattr(lib, f"ipx_eval_stencil_perm_{t}")
+        f.restype = C.c_int
+        f.argtypes = [i32, C.POINTER(vp), i64, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), vp, i32,
+                      C.c_double, i32, C.POINTER(Params), i32, vp, vp, vp, vp]
         f = getattr(lib, f"ipx_cell_sort_{t}")
         f.restype = C.c_int
         f.argtypes = [i32, C.POINTER(vp), i64, C.POINTER(vp), C.POINTER(i32), i32, C.POINTER(Params), i32,

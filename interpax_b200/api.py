@@ -375,6 +375,42 @@ def _cell_sort_dev(ndim, qs, knots, ns, periodic_mask, params):
     return order, out
 
 
+def _presorted_stencil(fallback, ndim, knots, sknots, ns, sort_ns, sort_mask, halo, code, c, mask, params):
+    """The pre-sorted call of the evaluation from f with its permutation passes folded into the
+    kernel: cell keys + radix sort (ipx_cell_order_records_*), then ONE launch that reads query
+    order[k] from the interleaved coordinate records and writes out[order[k]]
+    (ipx_eval_stencil_perm_*).  Bit-identical to the plain call; `fallback` serves what the stencil
+    kernels do not (knot vectors too long for shared memory)."""
+    lib = L.load()
+
+    def run(dq, dout, want_idx):
+        errorif(want_idx, NotImplementedError, "interval indices are not available with presort")
+        nq = dq[0].numel()
+        if nq == 0:
+            return fallback(dq, dout, False)
+        dev, dt = dq[0].device, dq[0].dtype
+        order = torch.empty(nq, dtype=torch.int32, device=dev)  # holds uint32 values
+        R = 4 if ndim == 3 else ndim
+        recs = torch.empty(nq * R, dtype=dt, device=dev)
+        ws = torch.empty(max(int(lib.ipx_cell_order_workspace_bytes(nq)), 256), dtype=torch.uint8, device=dev)
+        suf = _suffix(dq[0])
+        narr = (C.c_int32 * ndim)(*[int(n) for n in sort_ns])
+        L.check(getattr(lib, f"ipx_cell_order_records_{suf}")(
+            ndim, _ptr_array(dq), nq, _ptr_array(knots), narr, sort_mask, C.byref(params), 0, _ptr(order),
+            _ptr(recs), _ptr(ws), _stream()), "ipx_cell_order_records")
+        out = dout if dout is not None else torch.empty((nq, 1), dtype=dt, device=dev)
+        narr2 = (C.c_int32 * ndim)(*[int(n) for n in ns])
+        rc = getattr(lib, f"ipx_eval_stencil_perm_{suf}")(
+            ndim, _ptr_array(dq), nq, _ptr_array(knots), _ptr_array(sknots), narr2, _ptr(halo), code, float(c), mask,
+            C.byref(params), 0, _ptr(order), _ptr(recs), _ptr(out), _stream())
+        if rc == L.IPX_EUNSUPPORTED:
+            return fallback(dq, dout, False)
+        L.check(rc, "ipx_eval_stencil_perm")
+        return out, None
+
+    return run
+
+
 def _presorted(launch, ndim, knots, ns, mask, params, batch):
     """Wrap `launch` so that it visits the queries in cell order: gather -> evaluate -> scatter
     (results are bit-identical to the plain call; only the memory access pattern changes)."""
@@ -761,8 +797,10 @@ def _interp(ndim, qs, knots, f, method, derivative, extrap, period, kwargs, retu
 
         if presort:
             # the cell sort sees the padded knots as they are: wrap-only axes of padded extent
-            launch_st = _presorted(launch_st, ndim, sk, [n + (2 if per[ax] else 0) for ax, n in enumerate(sns)],
-                                   sum(L.IPX_WRAP_ONLY(ax) for ax in range(ndim) if per[ax]), params, batch)
+            pns = [n + (2 if per[ax] else 0) for ax, n in enumerate(sns)]
+            pmask = sum(L.IPX_WRAP_ONLY(ax) for ax in range(ndim) if per[ax])
+            launch_st = _presorted_stencil(_presorted(launch_st, ndim, sk, pns, pmask, params, batch), ndim, sk,
+                                           [None] * ndim, sns, pns, pmask, halo, code, cten, smask, params)
         return _execute(io, qs, launch_st, batch, fshape_user[ndim:], out_arg, return_index)
     if mclass == L.IPX_CUBIC:
         missing = [n for n in names[1:] if tabs[n] is None]
@@ -1596,7 +1634,14 @@ class _InterpolatorND:
             return launch_records(dq, dout, want_idx)
 
         if presort:
-            launch = _presorted(launch, ndim, kuse, ns, mask, params, batch)
+            plain = _presorted(launch, ndim, kuse, ns, mask, params, batch)
+            if self._halo is not None and batch == 1:
+                launch = _presorted_stencil(plain, ndim, kuse, self._knots, ns, ns, mask, self._halo,
+                                            _STENCIL_METHODS[self.method],
+                                            float(self._kwargs.get("c", 0)) if self.method == "cardinal" else 0.0,
+                                            mask, params)
+            else:
+                launch = plain
         res = _execute(io, qs, launch, batch, self._fshape[ndim:], out, return_index)
         if (self._halo is not None and not st.complex and io.want_torch and len(self._plans) < 16
                 and all(isinstance(d, (int, np.integer)) for d in derivative)):

@@ -345,7 +345,8 @@ static void radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_
 template <typename T, int ND>
 static int launch_cell_order(const T* const* q, int64_t nq, const T* const* knots, const int32_t* n,
                              int32_t periodic_mask, const ipx_params* params, int32_t params_on_device,
-                             uint32_t* order, T* const* q_sorted, void* workspace, cudaStream_t s) {
+                             uint32_t* order, T* const* q_sorted, void* workspace, cudaStream_t s,
+                             T* recs_out = nullptr) {
   KeyArgs<T, ND> a;
   double cells = 1.0;
   for (int ax = 0; ax < ND; ++ax) {
@@ -382,7 +383,7 @@ static int launch_cell_order(const T* const* q, int64_t nq, const T* const* knot
   uint32_t* sums = reinterpret_cast<uint32_t*>(ws + p.off_sums);
   int64_t need = (nq + 255) / 256;
   int64_t cap = (int64_t)sm_count() * 16;
-  T* recs = nullptr;
+  T* recs = recs_out;  // the interleaved coordinate records, left to the caller (no gather)
   if (q_sorted != nullptr) {
     for (int ax = 0; ax < ND; ++ax)
       if (q_sorted[ax] == nullptr) return IPX_EINVAL;
@@ -489,16 +490,16 @@ template <typename T>
 static int cell_order_dispatch(int32_t ndim, const T* const* q, int64_t nq, const T* const* knots,
                                const int32_t* n, int32_t periodic_mask, const ipx_params* params,
                                int32_t params_on_device, uint32_t* order, T* const* q_sorted,
-                               void* workspace, void* stream) {
+                               void* workspace, void* stream, T* recs_out = nullptr) {
   if (ndim < 1 || ndim > 3 || q == nullptr || knots == nullptr || n == nullptr || params == nullptr || nq < 0)
     return IPX_EINVAL;
   if (nq >= 4294967296LL) return IPX_EUNSUPPORTED;
   if (nq == 0) return IPX_OK;
   if (order == nullptr || workspace == nullptr) return IPX_EINVAL;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (ndim == 1) return launch_cell_order<T, 1>(q, nq, knots, n, periodic_mask, params, params_on_device, order, q_sorted, workspace, s);
-  if (ndim == 2) return launch_cell_order<T, 2>(q, nq, knots, n, periodic_mask, params, params_on_device, order, q_sorted, workspace, s);
-  return launch_cell_order<T, 3>(q, nq, knots, n, periodic_mask, params, params_on_device, order, q_sorted, workspace, s);
+  if (ndim == 1) return launch_cell_order<T, 1>(q, nq, knots, n, periodic_mask, params, params_on_device, order, q_sorted, workspace, s, recs_out);
+  if (ndim == 2) return launch_cell_order<T, 2>(q, nq, knots, n, periodic_mask, params, params_on_device, order, q_sorted, workspace, s, recs_out);
+  return launch_cell_order<T, 3>(q, nq, knots, n, periodic_mask, params, params_on_device, order, q_sorted, workspace, s, recs_out);
 }
 
 }  // namespace ipx
@@ -534,6 +535,18 @@ extern "C" int ipx_cell_sort_f64(int32_t ndim, const double* const* q, int64_t n
   return ipx::cell_order_dispatch<double>(ndim, q, nq, knots, n, periodic_mask, params, params_on_device, order,
                                           q_sorted, workspace, stream);
 }
+#define IPX_DEFINE_ORDER_RECORDS(SUF, T)                                                                          \
+  extern "C" int ipx_cell_order_records_##SUF(int32_t ndim, const T* const* q, int64_t nq, const T* const* knots, \
+                                              const int32_t* n, int32_t periodic_mask, const ipx_params* params,  \
+                                              int32_t params_on_device, uint32_t* order, T* records,              \
+                                              void* workspace, void* stream) {                                    \
+    if (records == nullptr && nq > 0) return IPX_EINVAL;                                                          \
+    return ipx::cell_order_dispatch<T>(ndim, q, nq, knots, n, periodic_mask, params, params_on_device, order,     \
+                                       nullptr, workspace, stream, records);                                      \
+  }
+IPX_DEFINE_ORDER_RECORDS(f32, float)
+IPX_DEFINE_ORDER_RECORDS(f64, double)
+
 extern "C" size_t ipx_cell_sort_workspace_bytes(int32_t ndim, int64_t nq, int32_t elem_size) {
   if (nq < 0) nq = 0;
   const size_t rec = ndim == 3 ? 4 : (ndim < 1 ? 1 : (size_t)ndim);

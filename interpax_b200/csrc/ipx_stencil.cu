@@ -81,6 +81,12 @@ template <typename T, int ND> struct StArgs {
   int32_t cardinal;  // 0: _cubic1, 1: _cardinal
   const int32_t* __restrict__ flag;  // NULL, or: run only if bit *flag of `accept` is set (device-side
   uint32_t accept;                   // choice of kernel shape and table layout, see launch_stencil)
+  // Visiting order (ipx_eval_stencil_perm_*): query k of the launch is the caller's query order[k],
+  // its coordinates come from the interleaved records of ipx_cell_order_records_* (one sector per
+  // query) and its result goes to out[order[k]] -- the gather and scatter passes of a pre-sorted
+  // call folded into the evaluation.  Sparse shape only.
+  const uint32_t* __restrict__ order;
+  const T* __restrict__ recs;
   ipx_params hp;
   const ipx_params* dp;
 };
@@ -572,11 +578,33 @@ stencil_sparse_kernel(const __grid_constant__ StArgs<T, ND> a) {
   const bool want_idx = a.idx_out != nullptr;
   StRounds R((a.nq + 31) / 32);
   for (int64_t rnd = R.begin(); rnd >= 0; rnd = R.next(rnd)) {
-    const int64_t qi = rnd * 32 + lane;
+    int64_t qi = rnd * 32 + lane;
     if (qi >= a.nq) continue;
     T raw[ND];
+    if (a.order != nullptr) {
+      qi = (int64_t)__ldcs(a.order + qi);
+      constexpr int R = ND == 3 ? 4 : ND;
+      const T* r = a.recs + qi * R;
+      if constexpr (R == 1) {
+        raw[0] = __ldg(r);
+      } else if constexpr (sizeof(T) == 8) {
 #pragma unroll
-    for (int ax = 0; ax < ND; ++ax) raw[ax] = __ldcs(a.ax[ax].q + qi);
+        for (int m = 0; m < ND; m += 2) {
+          const double2 v = __ldg(reinterpret_cast<const double2*>(r + m));
+          raw[m] = T(v.x);
+          if (m + 1 < ND) raw[m + 1 < ND ? m + 1 : m] = T(v.y);
+        }
+      } else if constexpr (R == 2) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(r));
+        raw[0] = T(v.x); raw[1] = T(v.y);
+      } else {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(r));
+        raw[0] = T(v.x); raw[1] = T(v.y); raw[ND - 1] = T(v.z);
+      }
+    } else {
+#pragma unroll
+      for (int ax = 0; ax < ND; ++ax) raw[ax] = __ldcs(a.ax[ax].q + qi);
+    }
     int ii[ND];
     unsigned fill;
     const T res = st_eval_one<T, ND, ORD0>(a, P, S, raw, ii, fill);
@@ -1186,8 +1214,10 @@ template <typename T, int ND>
 static int launch_stencil(const T* const* q, int64_t nq, const T* const* knots, const T* const* slope_knots,
                           const int32_t* n, const T* halo, const T* records, int32_t slope_method, double c,
                           int32_t periodic_mask, const ipx_params* params, int32_t params_on_device, T* out,
-                          int32_t* idx_out, int32_t hint, int32_t* workspace, void* stream) {
+                          int32_t* idx_out, int32_t hint, int32_t* workspace, void* stream,
+                          const uint32_t* order = nullptr, const T* coord_recs = nullptr) {
   if (nq < 0 || q == nullptr || knots == nullptr || n == nullptr || params == nullptr) return IPX_EINVAL;
+  if ((order == nullptr) != (coord_recs == nullptr)) return IPX_EINVAL;
   if (slope_method != IPX_SLOPE_CUBIC && slope_method != IPX_SLOPE_CARDINAL) return IPX_EUNSUPPORTED;
   if (hint < IPX_STENCIL_AUTO || hint > IPX_STENCIL_COLUMN) return IPX_EINVAL;
   if (nq == 0) return IPX_OK;
@@ -1235,6 +1265,8 @@ static int launch_stencil(const T* const* q, int64_t nq, const T* const* knots, 
   a.fac = T(1) - T(c);
   a.flag = nullptr;
   a.accept = 0;
+  a.order = order;
+  a.recs = coord_recs;
   if (params_on_device) {
     a.dp = params;
     a.hp = ipx_params{};
@@ -1245,6 +1277,10 @@ static int launch_stencil(const T* const* q, int64_t nq, const T* const* knots, 
   StDevice d;
   if (!st_device(d)) return IPX_ELAUNCH;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (order != nullptr) {
+    if ((reinterpret_cast<uintptr_t>(coord_recs) & 31) != 0) return IPX_EINVAL;
+    return st_launch_q<T, ND, false, 4>(a, d, s);  // the shape that takes its queries one per lane
+  }
   bool low_order = true;  // (the dense shape's hot loop covers derivative orders 0 and 1)
   if (!params_on_device)
     for (int ax = 0; ax < ND; ++ax) low_order = low_order && params->axis[ax].derivative <= 1;
@@ -1355,16 +1391,17 @@ static int launch_stencil_any(int32_t ndim, const T* const* q, int64_t nq, const
                               const T* const* slope_knots, const int32_t* n, const T* halo, const T* records,
                               int32_t slope_method,
                               double c, int32_t periodic_mask, const ipx_params* params, int32_t params_on_device,
-                              T* out, int32_t* idx_out, int32_t hint, int32_t* workspace, void* stream) {
+                              T* out, int32_t* idx_out, int32_t hint, int32_t* workspace, void* stream,
+                              const uint32_t* order = nullptr, const T* coord_recs = nullptr) {
   if (ndim == 1)
     return launch_stencil<T, 1>(q, nq, knots, slope_knots, n, halo, records, slope_method, c, periodic_mask,
-                                params, params_on_device, out, idx_out, hint, workspace, stream);
+                                params, params_on_device, out, idx_out, hint, workspace, stream, order, coord_recs);
   if (ndim == 2)
     return launch_stencil<T, 2>(q, nq, knots, slope_knots, n, halo, records, slope_method, c, periodic_mask,
-                                params, params_on_device, out, idx_out, hint, workspace, stream);
+                                params, params_on_device, out, idx_out, hint, workspace, stream, order, coord_recs);
   if (ndim == 3)
     return launch_stencil<T, 3>(q, nq, knots, slope_knots, n, halo, records, slope_method, c, periodic_mask,
-                                params, params_on_device, out, idx_out, hint, workspace, stream);
+                                params, params_on_device, out, idx_out, hint, workspace, stream, order, coord_recs);
   return IPX_EINVAL;
 }
 
@@ -1404,3 +1441,19 @@ extern "C" int ipx_eval_stencil_f64(int32_t ndim, const double* const* q, int64_
   return ipx::launch_stencil_any<double>(ndim, q, nq, knots, slope_knots, n, halo, records, slope_method, c, periodic_mask,
                                          params, params_on_device, out, idx_out, hint, workspace, stream);
 }
+
+// the pre-sorted call with its permutation passes folded in (see StArgs::order)
+#define IPX_DEFINE_STENCIL_PERM(SUF, T)                                                                            \
+  extern "C" int ipx_eval_stencil_perm_##SUF(int32_t ndim, const T* const* q, int64_t nq, const T* const* knots,   \
+                                             const T* const* slope_knots, const int32_t* n, const T* halo,         \
+                                             int32_t slope_method, double c, int32_t periodic_mask,                \
+                                             const ipx_params* params, int32_t params_on_device,                   \
+                                             const uint32_t* order, const T* coord_records, T* out,                \
+                                             void* stream) {                                                       \
+    if (order == nullptr || coord_records == nullptr) return IPX_EINVAL;                                           \
+    return ipx::launch_stencil_any<T>(ndim, q, nq, knots, slope_knots, n, halo, nullptr, slope_method, c,          \
+                                      periodic_mask, params, params_on_device, out, nullptr, IPX_STENCIL_SPARSE,   \
+                                      nullptr, stream, order, coord_records);                                      \
+  }
+IPX_DEFINE_STENCIL_PERM(f32, float)
+IPX_DEFINE_STENCIL_PERM(f64, double)

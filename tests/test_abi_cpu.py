@@ -41,7 +41,7 @@ def header_symbols():
         out.add(f"ipx_jvp_knots_tables_{t}")
         out.add(f"ipx_slopes_jvp_rows_{t}")
         out.add(f"ipx_cubic2_solve_{t}")
-    return {n for n in out if not n.startswith("ipx_eval") or re.fullmatch(r"ipx_eval([123]d|_stencil)_f(32|64)", n)}
+    return {n for n in out if not n.startswith("ipx_eval") or re.fullmatch(r"ipx_eval([123]d|_stencil|_stencil_perm)_f(32|64)", n)}
 
 
 def test_library_exports_every_declared_symbol():

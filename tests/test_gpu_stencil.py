@@ -353,3 +353,45 @@ def test_small_calls_reuse_a_call_plan():
     assert isinstance(rnp, torch.Tensor) or isinstance(rnp, np.ndarray)
     rs = ip(xq.t(), yq.t())
     assert rs.shape == (50, 7) and same_bits(rs.t().cpu().numpy(), ip(xq, yq).cpu().numpy())
+
+
+@pytest.mark.parametrize("ndim", [1, 2, 3])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_presort_folded_into_the_evaluation_is_bitwise_the_plain_call(ndim, dtype):
+    """presort=True on the evaluation from f: cell keys + radix sort, then ONE kernel that reads query
+    order[k] from the interleaved coordinate records and writes out[order[k]]
+    (ipx_eval_stencil_perm_*).  Same bits as the plain call on the one-query-per-lane shape, in the
+    caller's order: periodic axes in both conventions, fills, NaN queries, odd counts."""
+    from interpax_b200 import _lib as L
+    from interpax_b200 import api
+    rng = np.random.default_rng(700 + ndim)
+    ns = [41, 33, 27][:ndim]
+    knots = [np.sort(rng.uniform(0.0, 2.0, n)).astype(dtype) for n in ns]
+    f = rng.normal(size=ns).astype(dtype)
+    nq = 150_001
+    qs = [rng.uniform(-0.4, 2.5, nq).astype(dtype) for _ in range(ndim)]
+    qs[0][11] = np.nan
+    cls = (ipx.Interpolator1D, ipx.Interpolator2D, ipx.Interpolator3D)[ndim - 1]
+    fun = (ipx.interp1d, ipx.interp2d, ipx.interp3d)[ndim - 1]
+    old = api.stencil_hint
+    try:
+        api.stencil_hint = L.IPX_STENCIL_SPARSE
+        for method, extrap, period, deriv in (("cubic", (True, 0.5), None, 0), ("cardinal", False, 2.2, 1),
+                                              ("catmull-rom", True, 2.2, 0)):
+            per = period if ndim == 1 or period is None else (period,) + (None,) * (ndim - 1)
+            d = deriv if ndim == 1 else (deriv,) + (0,) * (ndim - 1)
+            dd = (deriv,) + (0,) * (ndim - 1)
+            kw = {"c": 0.3} if method == "cardinal" else {}
+            ip = cls(*knots, f, method, extrap, per, **kw)
+            assert ip._halo is not None
+            a = ip(*qs, *dd)
+            b = ip(*qs, *dd, presort=True)
+            assert np.array_equal(np.isnan(a), np.isnan(b))
+            m = ~np.isnan(a)
+            assert np.array_equal(a[m], b[m]), (method, "class")
+            a = fun(*qs, *knots, f, method, d, extrap, per, **kw)
+            b = fun(*qs, *knots, f, method, d, extrap, per, presort=True, **kw)
+            m = ~np.isnan(a)
+            assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[m], b[m]), (method, "functional")
+    finally:
+        api.stencil_hint = old
