@@ -315,6 +315,18 @@ __device__ __forceinline__ void hermite_weights_t(T t, T dx, T dxi, int order, T
 }
 template <typename T, bool ORD0>
 __device__ __forceinline__ void hermite_weights_r(T q, T x0, T x1, int order, T dxi, T w[4]) {
+  if (ORD0 || order <= 0) {
+    // order 0, factored, with (t - 1) dx formed as q - x1 (the same quantity in one rounding):
+    // 10 FP64 operations per axis, the local coordinate included
+    const T t = (q - x0) * dxi;
+    const T t2 = t * t;
+    const T u = q - x1;  // (a zero-width cell has 1 / dx = 0, so t = 0 and both slope weights vanish as before)
+    w[1] = t2 * fma(T(-2), t, T(3));
+    w[0] = T(1) - w[1];
+    w[3] = t2 * u;
+    w[2] = (t2 - t) * u;
+    return;
+  }
   hermite_weights_t<T, ORD0>((q - x0) * dxi, x1 - x0, dxi, order, w);
 }
 
