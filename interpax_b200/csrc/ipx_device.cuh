@@ -148,9 +148,17 @@ __device__ __forceinline__ void axis_consts(const AxisDesc<T>& A, AxisConst<T>& 
 }
 
 template <typename T>
+__device__ __forceinline__ void locate_value(const AxisDesc<T>& A, const AxisConst<T>& C,
+                                             const ipx_axis_params& P, T q, AxisLoc<T>& L);
+template <typename T>
 __device__ __forceinline__ void locate(const AxisDesc<T>& A, const AxisConst<T>& C,
                                        const ipx_axis_params& P, int64_t qi, AxisLoc<T>& L) {
-  T q = A.q[qi];
+  locate_value(A, C, P, A.q[qi], L);
+}
+// the same for a coordinate already in a register
+template <typename T>
+__device__ __forceinline__ void locate_value(const AxisDesc<T>& A, const AxisConst<T>& C,
+                                             const ipx_axis_params& P, T q, AxisLoc<T>& L) {
   if (A.wrap) q = py_mod(q, T(fabs(P.period)));
   L.q = q;
   L.i = bin_index(A.knots, A.nk, q, C.x_first, C.inv_h, L.x0, L.x1);

@@ -64,12 +64,24 @@ __global__ void cell_key_kernel(const KeyArgs<T, ND> a, uint32_t* __restrict__ k
   if (threadIdx.x == 32) params_s = a.dp ? *a.dp : a.hp;
   __syncthreads();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.nq; e += stride) {
+  // (the coordinates of the thread's NEXT element are requested before the current one is located:
+  // the kernel waits on these loads, 66 % of its stall samples)
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  T qn[ND];
+#pragma unroll
+  for (int ax = 0; ax < ND; ++ax) qn[ax] = e < a.nq ? __ldcs(a.ax[ax].q + e) : T(0);
+  for (; e < a.nq; e += stride) {
+    T qc[ND];
+#pragma unroll
+    for (int ax = 0; ax < ND; ++ax) qc[ax] = qn[ax];
+    const int64_t en = e + stride;
+#pragma unroll
+    for (int ax = 0; ax < ND; ++ax) qn[ax] = en < a.nq ? __ldcs(a.ax[ax].q + en) : T(0);
     uint32_t key = 0;
 #pragma unroll
     for (int ax = 0; ax < ND; ++ax) {
       AxisLoc<T> L;
-      locate(a.ax[ax], consts[ax], params_s.axis[ax], e, L);
+      locate_value(a.ax[ax], consts[ax], params_s.axis[ax], qc[ax], L);
       uint32_t c = (uint32_t)(L.i - 1);
       if (c >= a.cells[ax]) c -= a.cells[ax];
       key += c * a.stride[ax];
@@ -80,7 +92,7 @@ __global__ void cell_key_kernel(const KeyArgs<T, ND> a, uint32_t* __restrict__ k
       constexpr int R = CoordRec<ND>::kLen;
       T c[R];
 #pragma unroll
-      for (int ax = 0; ax < R; ++ax) c[ax] = ax < ND ? a.ax[ax < ND ? ax : 0].q[e] : T(0);
+      for (int ax = 0; ax < R; ++ax) c[ax] = ax < ND ? qc[ax < ND ? ax : 0] : T(0);
       T* r = recs + e * R;
       if constexpr (R == 1) {
         r[0] = c[0];
@@ -223,7 +235,10 @@ __global__ void scan_add_kernel(uint32_t* __restrict__ data, int64_t count, cons
 // walks them 32 at a time in order, so rank-within-warp preserves the input order.  Items are
 // first placed in shared memory in digit order, then written out: consecutive threads write
 // consecutive addresses of a digit's run instead of 32 scattered words per warp.
-__global__ void __launch_bounds__(kSortThreads)
+#ifndef IPX_SORT_MINBLOCKS
+#define IPX_SORT_MINBLOCKS 4  // 64 registers: four blocks per SM (the kernel waits on its loads: 1.21 -> 0.9 ms per pass of 1e8 pairs)
+#endif
+__global__ void __launch_bounds__(kSortThreads, IPX_SORT_MINBLOCKS)
 radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, int64_t n,
                      int shift, const uint32_t* __restrict__ offsets, int nblocks,
                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
